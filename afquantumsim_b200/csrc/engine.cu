@@ -1,0 +1,587 @@
+// engine.cu — C ABI of libaqs_engine.so (see include/aqs_engine.h).
+// State management, per-gate dispatch, measurement entry points, timers.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "aqs_engine.h"
+#include "engine_internal.h"
+#include "gate_kernels.cuh"
+#include "measure_kernels.cuh"
+
+namespace aqs {
+
+static thread_local std::string t_err;
+static bool g_inited = false;
+static int g_device = 0;
+static int g_sm_count = 148;
+static size_t g_hbm_bytes = 0;
+static std::atomic<uint64_t> c_launches{0}, c_ops{0}, c_h2d{0}, c_d2h{0};
+
+int fail(int code, const std::string& msg) {
+    t_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at engine line %d: %s", (int)e, cudaGetErrorString(e), line, what);
+    t_err = buf;
+    return e == cudaErrorMemoryAllocation ? AQS_ERR_NOMEM : AQS_ERR_CUDA;
+}
+void count_launch(uint64_t n) { c_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_ops(uint64_t n) { c_ops.fetch_add(n, std::memory_order_relaxed); }
+int sm_count() { return g_sm_count; }
+
+#define CUDA_TRY(x)                                                           \
+    do {                                                                      \
+        cudaError_t e_ = (x);                                                 \
+        if (e_ != cudaSuccess) return aqs::fail_cuda(e_, #x, __LINE__);       \
+    } while (0)
+#define REQUIRE_INIT()                                                                          \
+    do {                                                                                        \
+        if (!aqs::g_inited) return aqs::fail(AQS_ERR_STATE, "aqs_engine_init has not been called"); \
+    } while (0)
+#define REQUIRE(cond, msg)                                      \
+    do {                                                        \
+        if (!(cond)) return aqs::fail(AQS_ERR_INVALID, msg);    \
+    } while (0)
+
+static inline uint64_t qmask_to_pos(int n, uint64_t qmask) {
+    uint64_t m = 0;
+    for (int q = 0; q < n; ++q)
+        if (qmask >> q & 1ull) m |= 1ull << (n - 1 - q);
+    return m;
+}
+
+static void bitlist_from_mask(uint64_t mask, BitList& f) {
+    f.n = 0;
+    for (int p = 0; p < 64; ++p)
+        if (mask >> p & 1ull) f.pos[f.n++] = (uint8_t)p;
+}
+
+static inline bool is_one(aqs_c32 z) { return z.re == 1.f && z.im == 0.f; }
+static inline bool is_zero(aqs_c32 z) { return z.re == 0.f && z.im == 0.f; }
+
+// Canonical form of an op in bit-position space.
+int canonicalize(int n, const aqs_op& op, CanonOp& c) {
+    REQUIRE(op.kind >= AQS_OP_U2 && op.kind <= AQS_OP_SWAP, "unknown op kind");
+    REQUIRE(op.target >= 0 && op.target < n, "target qubit out of range");
+    const uint64_t all = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    REQUIRE((op.ctrl_mask & ~all) == 0, "control mask names a qubit outside the state");
+    REQUIRE(!(op.ctrl_mask >> op.target & 1ull), "control qubit cannot be the target qubit");
+    c.kind = op.kind;
+    c.p = n - 1 - op.target;
+    c.p2 = -1;
+    c.cmask = qmask_to_pos(n, op.ctrl_mask);
+    c.cval = qmask_to_pos(n, op.ctrl_value & op.ctrl_mask);
+    for (int i = 0; i < 4; ++i) c.m[i] = make_float2(op.m[i].re, op.m[i].im);
+    c.d0_one = false;
+    if (op.kind == AQS_OP_SWAP) {
+        REQUIRE(op.target2 >= 0 && op.target2 < n, "second swap qubit out of range");
+        REQUIRE(op.target2 != op.target, "cannot swap a qubit with itself");
+        REQUIRE(!(op.ctrl_mask >> op.target2 & 1ull), "control qubit cannot be a swap target");
+        c.p2 = n - 1 - op.target2;
+        if (c.p2 > c.p) std::swap(c.p, c.p2);
+    } else if (op.kind == AQS_OP_U2) {
+        // demote structured matrices so they run on the cheaper kernels
+        if (is_zero(op.m[1]) && is_zero(op.m[2])) c.kind = AQS_OP_DIAG;
+        else if (is_zero(op.m[0]) && is_zero(op.m[3]) && is_one(op.m[1]) && is_one(op.m[2])) c.kind = AQS_OP_X;
+    }
+    if (c.kind == AQS_OP_DIAG) {
+        c.m[1] = c.m[2] = make_float2(0.f, 0.f);
+        c.d0_one = is_one(op.m[0]);
+    }
+    c.identity = (c.kind == AQS_OP_DIAG && c.d0_one && is_one(op.m[3]));
+    return AQS_OK;
+}
+
+// algorithmic HBM bytes of one op run alone
+double op_bytes(int n, const CanonOp& c) {
+    const double S = 8.0 * std::ldexp(1.0, n);
+    int nc = __builtin_popcountll(c.cmask);
+    double frac = std::ldexp(1.0, -nc);
+    if (c.identity) return 0.0;
+    if (c.kind == AQS_OP_DIAG && c.d0_one) frac *= 0.5;
+    if (c.kind == AQS_OP_SWAP) frac *= 0.5;
+    return 2.0 * S * frac;
+}
+
+template <typename K, typename A>
+static int launch_items(K kernel, const A& args, uint64_t items, int per_block, cudaStream_t st) {
+    const uint64_t blocks = (items + per_block - 1) / per_block;
+    if (blocks == 0) return AQS_OK;
+    if (blocks > 0x7fffffffull) return fail(AQS_ERR_INVALID, "grid too large");
+    kernel<<<(unsigned)blocks, kThreads, 0, st>>>(args);
+    count_launch(1);
+    return AQS_OK;
+}
+
+constexpr int kPairItems = 2;   // 2 x 2 x 16 B in flight per thread
+constexpr int kBit0Items = 4;
+constexpr int kDiagItems = 4;
+
+int launch_canon(float2* a, int n, const CanonOp& c, cudaStream_t st) {
+    if (c.identity) return AQS_OK;
+    const uint64_t N = 1ull << n;
+    if (c.kind == AQS_OP_DIAG) {
+        DiagArgs A;
+        A.a = a; A.p = c.p; A.d0_one = c.d0_one ? 1 : 0; A.d0 = c.m[0]; A.d1 = c.m[3];
+        uint64_t fixedmask = c.cmask;
+        A.off = c.cval;
+        if (c.d0_one) { fixedmask |= 1ull << c.p; A.off |= 1ull << c.p; }
+        if (!(fixedmask & 1ull) && n >= 1 && N >= 2) {
+            bitlist_from_mask(fixedmask | 1ull, A.fixed);
+            A.n_items = N >> A.fixed.n;
+            return launch_items(k_diag<2, kDiagItems>, A, A.n_items, kThreads * kDiagItems, st);
+        }
+        bitlist_from_mask(fixedmask, A.fixed);
+        A.n_items = N >> A.fixed.n;
+        return launch_items(k_diag<1, kDiagItems>, A, A.n_items, kThreads * kDiagItems, st);
+    }
+    PairArgs A;
+    A.a = a;
+    A.m00 = c.m[0]; A.m01 = c.m[1]; A.m10 = c.m[2]; A.m11 = c.m[3];
+    const bool perm = (c.kind == AQS_OP_X || c.kind == AQS_OP_SWAP);
+    uint64_t fixedmask = c.cmask | (1ull << c.p);
+    if (c.kind == AQS_OP_SWAP) {
+        fixedmask |= 1ull << c.p2;
+        A.offA = c.cval | (1ull << c.p);
+        A.offB = c.cval | (1ull << c.p2);
+    } else {
+        A.offA = c.cval;
+        A.offB = c.cval | (1ull << c.p);
+    }
+    if (c.kind != AQS_OP_SWAP && c.p == 0) {
+        // pair inside one 128-bit vector
+        bitlist_from_mask(fixedmask, A.fixed);
+        A.n_items = N >> A.fixed.n;
+        if (perm) return launch_items(k_pair_bit0<MK_PERM, kBit0Items>, A, A.n_items, kThreads * kBit0Items, st);
+        return launch_items(k_pair_bit0<MK_GENERAL, kBit0Items>, A, A.n_items, kThreads * kBit0Items, st);
+    }
+    if (!(fixedmask & 1ull)) {
+        bitlist_from_mask(fixedmask | 1ull, A.fixed);
+        A.n_items = N >> A.fixed.n;
+        if (perm) return launch_items(k_pair<2, MK_PERM, kPairItems>, A, A.n_items, kThreads * kPairItems, st);
+        return launch_items(k_pair<2, MK_GENERAL, kPairItems>, A, A.n_items, kThreads * kPairItems, st);
+    }
+    bitlist_from_mask(fixedmask, A.fixed);
+    A.n_items = N >> A.fixed.n;
+    if (perm) return launch_items(k_pair<1, MK_PERM, kPairItems>, A, A.n_items, kThreads * kPairItems, st);
+    return launch_items(k_pair<1, MK_GENERAL, kPairItems>, A, A.n_items, kThreads * kPairItems, st);
+}
+
+static int ensure_scratch(aqs_state_s* s, size_t bytes) {
+    if (s->scratch_bytes >= bytes) return AQS_OK;
+    if (s->scratch) cudaFree(s->scratch);
+    s->scratch = nullptr; s->scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s->scratch, bytes));
+    s->scratch_bytes = bytes;
+    return AQS_OK;
+}
+
+static unsigned stream_blocks(uint64_t work_threads) {
+    uint64_t b = (work_threads + 255) / 256;
+    uint64_t cap = (uint64_t)g_sm_count * 8;
+    return (unsigned)std::max<uint64_t>(1, std::min(b, cap));
+}
+
+}  // namespace aqs
+
+using namespace aqs;
+
+extern "C" {
+
+int aqs_engine_abi_version(void) { return AQS_ENGINE_ABI_VERSION; }
+const char* aqs_last_error(void) { return t_err.c_str(); }
+
+int aqs_engine_init(int device) {
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    REQUIRE(count > 0, "no CUDA device visible");
+    REQUIRE(device >= 0 && device < count, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    g_device = device;
+    g_sm_count = prop.multiProcessorCount;
+    g_hbm_bytes = prop.totalGlobalMem;
+    if (prop.major < 10) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+        return fail(AQS_ERR_STATE, buf);
+    }
+    int rc = aqs::fused_init();
+    if (rc != AQS_OK) return rc;
+    g_inited = true;
+    return AQS_OK;
+}
+
+int aqs_engine_shutdown(void) {
+    g_inited = false;
+    return AQS_OK;
+}
+
+int aqs_engine_device(int* device, int* sms, size_t* hbm) {
+    REQUIRE_INIT();
+    if (device) *device = g_device;
+    if (sms) *sms = g_sm_count;
+    if (hbm) *hbm = g_hbm_bytes;
+    return AQS_OK;
+}
+
+int aqs_state_create(int n, aqs_state_t* out) {
+    REQUIRE_INIT();
+    REQUIRE(out != nullptr, "null output handle");
+    REQUIRE(n >= 1 && n <= AQS_MAX_QUBITS, "qubit count must be in [1, AQS_MAX_QUBITS]");
+    CUDA_TRY(cudaSetDevice(g_device));
+    aqs_state_s* s = new (std::nothrow) aqs_state_s();
+    if (!s) return fail(AQS_ERR_NOMEM, "host allocation failed");
+    s->n = n;
+    s->N = 1ull << n;
+    const size_t bytes = std::max<size_t>(s->N * sizeof(float2), 16);
+    cudaError_t e = cudaMalloc((void**)&s->d, bytes);
+    if (e != cudaSuccess) { delete s; return fail_cuda(e, "cudaMalloc(state)", __LINE__); }
+    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFree(s->d); delete s; return fail_cuda(e, "cudaStreamCreate", __LINE__); }
+    s->own_stream = true;
+    *out = s;
+    return aqs_state_set_basis(s, 0);
+}
+
+int aqs_state_destroy(aqs_state_t s) {
+    if (!s) return AQS_OK;
+    cudaStreamSynchronize(s->stream);
+    if (s->scratch) cudaFree(s->scratch);
+    if (s->d) cudaFree(s->d);
+    if (s->own_stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return AQS_OK;
+}
+
+int aqs_state_clone(aqs_state_t src, aqs_state_t* out) {
+    REQUIRE_INIT();
+    REQUIRE(src && out, "null handle");
+    int rc = aqs_state_create(src->n, out);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    CUDA_TRY(cudaMemcpyAsync((*out)->d, src->d, src->N * sizeof(float2), cudaMemcpyDeviceToDevice, (*out)->stream));
+    return AQS_OK;
+}
+
+int aqs_state_qubits(aqs_state_t s, int* n) {
+    REQUIRE(s && n, "null handle");
+    *n = s->n;
+    return AQS_OK;
+}
+
+int aqs_state_set_basis(aqs_state_t s, uint64_t index) {
+    REQUIRE_INIT();
+    REQUIRE(s, "null handle");
+    REQUIRE(index < s->N, "basis index out of range");
+    CUDA_TRY(cudaMemsetAsync(s->d, 0, s->N * sizeof(float2), s->stream));
+    k_set_one<<<1, 1, 0, s->stream>>>(s->d, index);
+    count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return AQS_OK;
+}
+
+int aqs_state_set_product(aqs_state_t s, const aqs_c32* q) {
+    REQUIRE_INIT();
+    REQUIRE(s && q, "null argument");
+    ProductArgs P;
+    P.n = s->n;
+    for (int k = 0; k < s->n; ++k) {
+        P.q[k][0] = make_float2(q[2 * k].re, q[2 * k].im);
+        P.q[k][1] = make_float2(q[2 * k + 1].re, q[2 * k + 1].im);
+    }
+    k_set_product<<<stream_blocks(s->N), 256, 0, s->stream>>>(s->d, s->N, P);
+    count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return AQS_OK;
+}
+
+int aqs_state_set_identity(aqs_state_t s) {
+    REQUIRE_INIT();
+    REQUIRE(s, "null handle");
+    REQUIRE((s->n & 1) == 0, "identity needs an even qubit count (2m)");
+    CUDA_TRY(cudaMemsetAsync(s->d, 0, s->N * sizeof(float2), s->stream));
+    k_set_diag_ones<<<stream_blocks(1ull << (s->n / 2)), 256, 0, s->stream>>>(s->d, s->n / 2);
+    count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return AQS_OK;
+}
+
+int aqs_state_upload(aqs_state_t s, const aqs_c32* host, uint64_t offset, uint64_t count) {
+    REQUIRE_INIT();
+    REQUIRE(s && host, "null argument");
+    REQUIRE(offset <= s->N && count <= s->N - offset, "range outside the state");
+    CUDA_TRY(cudaMemcpyAsync(s->d + offset, host, count * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    c_h2d += count * sizeof(float2);
+    return AQS_OK;
+}
+
+int aqs_state_download(aqs_state_t s, aqs_c32* host, uint64_t offset, uint64_t count) {
+    REQUIRE_INIT();
+    REQUIRE(s && host, "null argument");
+    REQUIRE(offset <= s->N && count <= s->N - offset, "range outside the state");
+    CUDA_TRY(cudaMemcpyAsync(host, s->d + offset, count * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    c_d2h += count * sizeof(float2);
+    return AQS_OK;
+}
+
+int aqs_state_get_amp(aqs_state_t s, uint64_t index, aqs_c32* out) { return aqs_state_download(s, out, index, 1); }
+
+int aqs_state_device_ptr(aqs_state_t s, void** dptr) {
+    REQUIRE(s && dptr, "null argument");
+    *dptr = s->d;
+    return AQS_OK;
+}
+
+int aqs_state_set_stream(aqs_state_t s, void* stream) {
+    REQUIRE(s, "null handle");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)stream;
+    s->own_stream = false;
+    return AQS_OK;
+}
+
+int aqs_state_get_stream(aqs_state_t s, void** stream) {
+    REQUIRE(s && stream, "null argument");
+    *stream = (void*)s->stream;
+    return AQS_OK;
+}
+
+int aqs_sync(aqs_state_t s) {
+    REQUIRE(s, "null handle");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return AQS_OK;
+}
+
+int aqs_apply_op(aqs_state_t s, const aqs_op* op) {
+    REQUIRE_INIT();
+    REQUIRE(s && op, "null argument");
+    CanonOp c;
+    int rc = canonicalize(s->n, *op, c);
+    if (rc) return rc;
+    rc = launch_canon(s->d, s->n, c, s->stream);
+    if (rc) return rc;
+    count_ops(1);
+    CUDA_TRY(cudaGetLastError());
+    return AQS_OK;
+}
+
+int aqs_apply_ops(aqs_state_t s, const aqs_op* ops, uint64_t n_ops) {
+    REQUIRE_INIT();
+    REQUIRE(s && (ops || n_ops == 0), "null argument");
+    for (uint64_t i = 0; i < n_ops; ++i) {
+        int rc = aqs_apply_op(s, ops + i);
+        if (rc) return rc;
+    }
+    return AQS_OK;
+}
+
+// ---- probabilities / measurement ------------------------------------------------
+int aqs_norm2(aqs_state_t s, double* out) {
+    REQUIRE_INIT();
+    REQUIRE(s && out, "null argument");
+    int rc = ensure_scratch(s, 64);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->scratch, 0, sizeof(double), s->stream));
+    k_norm2<<<stream_blocks(s->N), 256, 0, s->stream>>>(s->d, s->N, (double*)s->scratch);
+    count_launch(1);
+    CUDA_TRY(cudaMemcpyAsync(out, s->scratch, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    c_d2h += 8;
+    return AQS_OK;
+}
+
+int aqs_scale(aqs_state_t s, float f) {
+    REQUIRE_INIT();
+    REQUIRE(s, "null handle");
+    k_scale<<<stream_blocks(s->N), 256, 0, s->stream>>>(s->d, s->N, f);
+    count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return AQS_OK;
+}
+
+int aqs_prob_fixed(aqs_state_t s, uint64_t qmask, uint64_t qvalue, uint64_t* out) {
+    REQUIRE_INIT();
+    REQUIRE(s && out, "null argument");
+    const uint64_t all = (1ull << s->n) - 1ull;
+    REQUIRE((qmask & ~all) == 0, "mask names a qubit outside the state");
+    int rc = ensure_scratch(s, 64);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->scratch, 0, sizeof(unsigned long long), s->stream));
+    k_prob_fixed<<<stream_blocks(s->N / 2), 256, 0, s->stream>>>(s->d, s->N, qmask_to_pos(s->n, qmask),
+                                                              qmask_to_pos(s->n, qvalue & qmask),
+                                                              (unsigned long long*)s->scratch);
+    count_launch(1);
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, s->scratch, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    c_d2h += 8;
+    *out = h;
+    return AQS_OK;
+}
+
+int aqs_qubit_prob1(aqs_state_t s, int qubit, double* out) {
+    REQUIRE(s && out, "null argument");
+    REQUIRE(qubit >= 0 && qubit < s->n, "qubit out of range");
+    uint64_t f = 0;
+    int rc = aqs_prob_fixed(s, 1ull << qubit, 1ull << qubit, &f);
+    if (rc) return rc;
+    *out = (double)f * 0x1p-62;
+    return AQS_OK;
+}
+
+int aqs_probabilities(aqs_state_t s, float* host_out, uint64_t offset, uint64_t count) {
+    REQUIRE_INIT();
+    REQUIRE(s && host_out, "null argument");
+    REQUIRE(offset <= s->N && count <= s->N - offset, "range outside the state");
+    if (count == 0) return AQS_OK;
+    float* tmp = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&tmp, count * sizeof(float)));
+    k_probabilities<<<stream_blocks(count), 256, 0, s->stream>>>(s->d + offset, count, tmp);
+    count_launch(1);
+    cudaError_t e = cudaMemcpyAsync(host_out, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail_cuda(e, "probabilities copy", __LINE__);
+    c_d2h += count * sizeof(float);
+    return AQS_OK;
+}
+
+int aqs_collapse_qubit(aqs_state_t s, int qubit, int outcome, float p) {
+    REQUIRE_INIT();
+    REQUIRE(s, "null handle");
+    REQUIRE(qubit >= 0 && qubit < s->n, "qubit out of range");
+    REQUIRE(outcome == 0 || outcome == 1, "outcome must be 0 or 1");
+    k_collapse<<<stream_blocks(s->N), 256, 0, s->stream>>>(s->d, s->N, 1ull << (s->n - 1 - qubit), outcome, p);
+    count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return AQS_OK;
+}
+
+static int sample_impl(aqs_state_t s, const float* u_host, uint64_t n_draws, uint64_t* out_host, uint32_t* hist_host) {
+    REQUIRE_INIT();
+    REQUIRE(s && (u_host || n_draws == 0), "null argument");
+    REQUIRE(n_draws <= 0x7fffffffull, "too many draws for one call");
+    const uint64_t tile_amps = std::min<uint64_t>(s->N, kTileAmps);
+    const uint64_t n_tiles = s->N / tile_amps;
+    // scratch layout: [tile sums: n_tiles u64][u: n_draws f32 (padded)][out: n_draws u64]
+    const size_t off_u = ((n_tiles * 8 + 255) / 256) * 256;
+    const size_t off_o = off_u + ((n_draws * 4 + 255) / 256) * 256;
+    const size_t need = off_o + n_draws * 8 + 256;
+    int rc = ensure_scratch(s, need);
+    if (rc) return rc;
+    char* base = (char*)s->scratch;
+    unsigned long long* sums = (unsigned long long*)base;
+    float* u_dev = (float*)(base + off_u);
+    unsigned long long* out_dev = (unsigned long long*)(base + off_o);
+    uint32_t* hist_dev = nullptr;
+    if (hist_host) {
+        CUDA_TRY(cudaMalloc((void**)&hist_dev, s->N * sizeof(uint32_t)));
+        cudaError_t e = cudaMemsetAsync(hist_dev, 0, s->N * sizeof(uint32_t), s->stream);
+        if (e != cudaSuccess) { cudaFree(hist_dev); return fail_cuda(e, "hist memset", __LINE__); }
+    }
+    k_tile_sums<<<(unsigned)n_tiles, 256, 0, s->stream>>>(s->d, tile_amps, sums);
+    k_scan_tiles<<<1, 1024, 0, s->stream>>>(sums, n_tiles);
+    count_launch(2);
+    cudaError_t e = cudaSuccess;
+    if (n_draws) {
+        e = cudaMemcpyAsync(u_dev, u_host, n_draws * 4, cudaMemcpyHostToDevice, s->stream);
+        c_h2d += n_draws * 4;
+        if (e == cudaSuccess) {
+            k_sample<<<(unsigned)n_draws, 256, 0, s->stream>>>(s->d, tile_amps, n_tiles, sums, u_dev,
+                                                              out_host ? out_dev : nullptr, hist_dev);
+            count_launch(1);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && out_host) {
+            e = cudaMemcpyAsync(out_host, out_dev, n_draws * 8, cudaMemcpyDeviceToHost, s->stream);
+            c_d2h += n_draws * 8;
+        }
+    }
+    if (e == cudaSuccess && hist_host) {
+        e = cudaMemcpyAsync(hist_host, hist_dev, s->N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
+        c_d2h += s->N * sizeof(uint32_t);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (hist_dev) cudaFree(hist_dev);
+    if (e != cudaSuccess) return fail_cuda(e, "sampling", __LINE__);
+    return AQS_OK;
+}
+
+int aqs_sample(aqs_state_t s, const float* u, uint64_t n, uint64_t* out) {
+    REQUIRE(out || n == 0, "null output");
+    return sample_impl(s, u, n, out, nullptr);
+}
+int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
+    REQUIRE(hist, "null histogram");
+    return sample_impl(s, u, n, nullptr, hist);
+}
+
+// ---- timers -------------------------------------------------------------------------
+struct aqs_timer_s {
+    cudaEvent_t a, b;
+};
+int aqs_timer_create(aqs_timer_t* out) {
+    REQUIRE_INIT();
+    REQUIRE(out, "null output");
+    aqs_timer_s* t = new (std::nothrow) aqs_timer_s();
+    if (!t) return fail(AQS_ERR_NOMEM, "host allocation failed");
+    CUDA_TRY(cudaEventCreate(&t->a));
+    CUDA_TRY(cudaEventCreate(&t->b));
+    *out = t;
+    return AQS_OK;
+}
+int aqs_timer_start(aqs_timer_t t, aqs_state_t s) {
+    REQUIRE(t && s, "null argument");
+    CUDA_TRY(cudaEventRecord(t->a, s->stream));
+    return AQS_OK;
+}
+int aqs_timer_stop(aqs_timer_t t, aqs_state_t s) {
+    REQUIRE(t && s, "null argument");
+    CUDA_TRY(cudaEventRecord(t->b, s->stream));
+    return AQS_OK;
+}
+int aqs_timer_elapsed_ms(aqs_timer_t t, double* ms) {
+    REQUIRE(t && ms, "null argument");
+    CUDA_TRY(cudaEventSynchronize(t->b));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, t->a, t->b));
+    *ms = f;
+    return AQS_OK;
+}
+int aqs_timer_destroy(aqs_timer_t t) {
+    if (!t) return AQS_OK;
+    cudaEventDestroy(t->a);
+    cudaEventDestroy(t->b);
+    delete t;
+    return AQS_OK;
+}
+
+int aqs_counters_get(aqs_counters* out) {
+    REQUIRE(out, "null output");
+    out->kernel_launches = c_launches.load();
+    out->gate_ops = c_ops.load();
+    out->h2d_bytes = c_h2d.load();
+    out->d2h_bytes = c_d2h.load();
+    return AQS_OK;
+}
+int aqs_counters_reset(void) {
+    c_launches = 0; c_ops = 0; c_h2d = 0; c_d2h = 0;
+    return AQS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+"""Synthetic circuits of BASELINE.json's configs, as plain gate tuples
+``(ClassName, *ctor_args)`` in the reference's constructor order.  Both the
+product path (afquantumsim_b200.aqs) and the test oracle consume this format."""
+from __future__ import annotations
+
+import numpy as np
+
+TWO_PI = 2.0 * np.pi
+
+
+def ghz(n: int):
+    """config 1: H{0} then CX{i,i+1}."""
+    return [("H", 0)] + [("CX", i, i + 1) for i in range(n - 1)]
+
+
+def brickwork(n: int, depth: int = 20, seed: int | None = None):
+    """config 3/5: per layer d, one random RotX/RotY/RotZ(theta) on every qubit
+    (theta ~ U[0, 2pi) as f32), then CX{q,q+1} for q = d mod 2, +2, ...
+    numpy PCG64(seed = n by default).  30 qubits x depth 20 = 600 rotations +
+    290 CX = 890 gate applications."""
+    rng = np.random.Generator(np.random.PCG64(n if seed is None else seed))
+    names = ("RotX", "RotY", "RotZ")
+    gates = []
+    for d in range(depth):
+        for q in range(n):
+            k = int(rng.integers(0, 3))
+            theta = float(np.float32(rng.random() * TWO_PI))
+            gates.append((names[k], q, theta))
+        for q in range(d % 2, n - 1, 2):
+            gates.append(("CX", q, q + 1))
+    return gates
+
+
+def qft(n: int):
+    """config 2/5: fourier_transform(n), src/quantum_algo.cpp:103-114."""
+    pi = np.float32(3.14159265358979323846)
+    gates = []
+    for i in range(n - 1, -1, -1):
+        gates.append(("H", i))
+        for j in range(i):
+            gates.append(("CPhase", j, i, float(pi / np.float32(1 << (i - j)))))
+    return gates

@@ -1,0 +1,184 @@
+/*
+ * abi_shim.c — CPU stand-in for libaqs_engine.so.   TEST INFRASTRUCTURE ONLY.
+ *
+ * Implements every entry point of include/aqs_engine.h on top of the oracle
+ * (aqs_oracle.c), so that the C++ host layer (afquantumsim_b200/host) — circuit
+ * construction, flattening of composite gates, measurement logic, the string
+ * grammar — can be exercised by `-m "not gpu"` tests in a container without a
+ * GPU.  It is built into oracle/_build/cpu_abi/libaqs_engine.so and is loaded
+ * ONLY by tests (via LD_LIBRARY_PATH / an explicit preload).  The product never
+ * loads it: afquantumsim_b200 always dlopens afquantumsim_b200/lib/libaqs_engine.so
+ * by absolute path, and that library has no CPU path.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "aqs_engine.h"
+
+typedef struct { float re, im; } c32;
+int orc_apply_prim(c32* a, int n, int kind, int p, int p2, uint64_t cmask, uint64_t cval, const c32* m);
+void orc_set_basis(c32* a, int n, uint64_t idx);
+void orc_set_product(c32* a, int n, const c32* q);
+void orc_probabilities(const c32* a, int n, float* out);
+uint64_t orc_prob_fixed(const c32* a, int n, uint64_t mask, uint64_t value);
+double orc_norm2(const c32* a, int n);
+void orc_collapse_qubit(c32* a, int n, int qubit, int outcome, float p);
+int orc_sample(const c32* a, int n, const float* u, uint64_t draws, uint64_t* out, int mode);
+
+struct aqs_state_s { int n; uint64_t N; c32* a; };
+struct aqs_plan_s { int n; uint64_t n_ops; aqs_op* ops; double bytes; };
+struct aqs_timer_s { struct timespec a, b; };
+
+static __thread char g_err[256];
+static int g_init = 0;
+static aqs_counters g_cnt;
+
+static int fail(int code, const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
+#define REQ(c, msg) do { if (!(c)) return fail(AQS_ERR_INVALID, msg); } while (0)
+
+const char* aqs_last_error(void) { return g_err; }
+int aqs_engine_abi_version(void) { return AQS_ENGINE_ABI_VERSION; }
+int aqs_engine_init(int device) { (void)device; g_init = 1; return AQS_OK; }
+int aqs_engine_shutdown(void) { g_init = 0; return AQS_OK; }
+int aqs_engine_device(int* d, int* sm, size_t* mem) { if (d) *d = -1; if (sm) *sm = 0; if (mem) *mem = 0; return AQS_OK; }
+
+int aqs_state_create(int n, aqs_state_t* out) {
+    if (!g_init) return fail(AQS_ERR_STATE, "aqs_engine_init has not been called");
+    REQ(out, "null output handle");
+    REQ(n >= 1 && n <= 30, "qubit count must be in [1, 30] (cpu shim)");
+    aqs_state_t s = (aqs_state_t)calloc(1, sizeof *s);
+    s->n = n; s->N = 1ULL << n;
+    s->a = (c32*)calloc(s->N, sizeof(c32));
+    if (!s->a) { free(s); return fail(AQS_ERR_NOMEM, "allocation failed"); }
+    s->a[0].re = 1.f;
+    *out = s;
+    return AQS_OK;
+}
+int aqs_state_destroy(aqs_state_t s) { if (s) { free(s->a); free(s); } return AQS_OK; }
+int aqs_state_clone(aqs_state_t src, aqs_state_t* out) {
+    REQ(src && out, "null handle");
+    int rc = aqs_state_create(src->n, out);
+    if (rc) return rc;
+    memcpy((*out)->a, src->a, src->N * sizeof(c32));
+    return AQS_OK;
+}
+int aqs_state_qubits(aqs_state_t s, int* n) { REQ(s && n, "null"); *n = s->n; return AQS_OK; }
+int aqs_state_set_basis(aqs_state_t s, uint64_t idx) { REQ(s, "null handle"); REQ(idx < s->N, "basis index out of range"); orc_set_basis(s->a, s->n, idx); return AQS_OK; }
+int aqs_state_set_product(aqs_state_t s, const aqs_c32* q) { REQ(s && q, "null"); orc_set_product(s->a, s->n, (const c32*)q); return AQS_OK; }
+int aqs_state_set_identity(aqs_state_t s) {
+    REQ(s, "null handle"); REQ((s->n & 1) == 0, "identity needs an even qubit count (2m)");
+    memset(s->a, 0, s->N * sizeof(c32));
+    uint64_t M = 1ULL << (s->n / 2);
+    for (uint64_t c = 0; c < M; ++c) s->a[c * M + c].re = 1.f;
+    return AQS_OK;
+}
+int aqs_state_upload(aqs_state_t s, const aqs_c32* h, uint64_t off, uint64_t cnt) {
+    REQ(s && h, "null"); REQ(off <= s->N && cnt <= s->N - off, "range outside the state");
+    memcpy(s->a + off, h, cnt * sizeof(c32)); g_cnt.h2d_bytes += cnt * 8; return AQS_OK;
+}
+int aqs_state_download(aqs_state_t s, aqs_c32* h, uint64_t off, uint64_t cnt) {
+    REQ(s && h, "null"); REQ(off <= s->N && cnt <= s->N - off, "range outside the state");
+    memcpy(h, s->a + off, cnt * sizeof(c32)); g_cnt.d2h_bytes += cnt * 8; return AQS_OK;
+}
+int aqs_state_get_amp(aqs_state_t s, uint64_t i, aqs_c32* out) { return aqs_state_download(s, out, i, 1); }
+int aqs_state_device_ptr(aqs_state_t s, void** p) { REQ(s && p, "null"); *p = s->a; return AQS_OK; }
+int aqs_state_set_stream(aqs_state_t s, void* st) { (void)s; (void)st; return AQS_OK; }
+int aqs_state_get_stream(aqs_state_t s, void** st) { (void)s; if (st) *st = NULL; return AQS_OK; }
+int aqs_sync(aqs_state_t s) { (void)s; return AQS_OK; }
+
+static uint64_t to_pos(int n, uint64_t qmask) {
+    uint64_t m = 0;
+    for (int q = 0; q < n; ++q) if (qmask >> q & 1ULL) m |= 1ULL << (n - 1 - q);
+    return m;
+}
+static int validate(int n, const aqs_op* op) {
+    REQ(op->kind >= AQS_OP_U2 && op->kind <= AQS_OP_SWAP, "unknown op kind");
+    REQ(op->target >= 0 && op->target < n, "target qubit out of range");
+    REQ((op->ctrl_mask >> n) == 0, "control mask names a qubit outside the state");
+    REQ(!(op->ctrl_mask >> op->target & 1ULL), "control qubit cannot be the target qubit");
+    if (op->kind == AQS_OP_SWAP) {
+        REQ(op->target2 >= 0 && op->target2 < n, "second swap qubit out of range");
+        REQ(op->target2 != op->target, "cannot swap a qubit with itself");
+        REQ(!(op->ctrl_mask >> op->target2 & 1ULL), "control qubit cannot be a swap target");
+    }
+    return AQS_OK;
+}
+int aqs_apply_op(aqs_state_t s, const aqs_op* op) {
+    REQ(s && op, "null argument");
+    int rc = validate(s->n, op);
+    if (rc) return rc;
+    int p2 = op->kind == AQS_OP_SWAP ? s->n - 1 - op->target2 : -1;
+    orc_apply_prim(s->a, s->n, op->kind, s->n - 1 - op->target, p2, to_pos(s->n, op->ctrl_mask),
+                   to_pos(s->n, op->ctrl_value & op->ctrl_mask), (const c32*)op->m);
+    g_cnt.gate_ops++; g_cnt.kernel_launches++;
+    return AQS_OK;
+}
+int aqs_apply_ops(aqs_state_t s, const aqs_op* ops, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) { int rc = aqs_apply_op(s, ops + i); if (rc) return rc; }
+    return AQS_OK;
+}
+
+int aqs_plan_build(int n, const aqs_op* ops, uint64_t n_ops, uint32_t flags, aqs_plan_t* out) {
+    (void)flags;
+    REQ(out, "null output handle"); REQ(n >= 1 && n <= AQS_MAX_QUBITS, "qubit count out of range");
+    for (uint64_t i = 0; i < n_ops; ++i) { int rc = validate(n, ops + i); if (rc) return rc; }
+    aqs_plan_t p = (aqs_plan_t)calloc(1, sizeof *p);
+    p->n = n; p->n_ops = n_ops;
+    p->ops = (aqs_op*)malloc(sizeof(aqs_op) * (n_ops ? n_ops : 1));
+    if (n_ops) memcpy(p->ops, ops, sizeof(aqs_op) * n_ops);
+    *out = p;
+    return AQS_OK;
+}
+int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
+    REQ(s && p, "null handle"); REQ(s->n == p->n, "plan and state have different qubit counts");
+    return aqs_apply_ops(s, p->ops, p->n_ops);
+}
+int aqs_plan_get_info(aqs_plan_t p, aqs_plan_info* info) {
+    REQ(p && info, "null"); memset(info, 0, sizeof *info);
+    info->n_ops = info->n_launches = info->n_single_ops = p->n_ops; info->n_qubits = p->n;
+    return AQS_OK;
+}
+int aqs_plan_destroy(aqs_plan_t p) { if (p) { free(p->ops); free(p); } return AQS_OK; }
+
+int aqs_norm2(aqs_state_t s, double* out) { REQ(s && out, "null"); *out = orc_norm2(s->a, s->n); return AQS_OK; }
+int aqs_scale(aqs_state_t s, float f) { REQ(s, "null"); for (uint64_t r = 0; r < s->N; ++r) { s->a[r].re *= f; s->a[r].im *= f; } return AQS_OK; }
+int aqs_prob_fixed(aqs_state_t s, uint64_t qm, uint64_t qv, uint64_t* out) {
+    REQ(s && out, "null"); REQ((qm >> s->n) == 0, "mask names a qubit outside the state");
+    *out = orc_prob_fixed(s->a, s->n, to_pos(s->n, qm), to_pos(s->n, qv & qm)); return AQS_OK;
+}
+int aqs_qubit_prob1(aqs_state_t s, int q, double* out) {
+    REQ(s && out, "null"); REQ(q >= 0 && q < s->n, "qubit out of range");
+    uint64_t f; aqs_prob_fixed(s, 1ULL << q, 1ULL << q, &f); *out = (double)f * 0x1p-62; return AQS_OK;
+}
+int aqs_probabilities(aqs_state_t s, float* out, uint64_t off, uint64_t cnt) {
+    REQ(s && out, "null"); REQ(off <= s->N && cnt <= s->N - off, "range outside the state");
+    float* tmp = (float*)malloc(sizeof(float) * s->N);
+    orc_probabilities(s->a, s->n, tmp); memcpy(out, tmp + off, cnt * sizeof(float)); free(tmp); return AQS_OK;
+}
+int aqs_collapse_qubit(aqs_state_t s, int q, int outcome, float p) {
+    REQ(s, "null"); REQ(q >= 0 && q < s->n, "qubit out of range"); REQ(outcome == 0 || outcome == 1, "outcome must be 0 or 1");
+    orc_collapse_qubit(s->a, s->n, q, outcome, p); return AQS_OK;
+}
+int aqs_sample(aqs_state_t s, const float* u, uint64_t n, uint64_t* out) {
+    REQ(s && (out || n == 0), "null"); if (n == 0) return AQS_OK;
+    return orc_sample(s->a, s->n, u, n, out, 0) ? fail(AQS_ERR_NOMEM, "sample") : AQS_OK;
+}
+int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
+    REQ(s && hist, "null"); memset(hist, 0, s->N * sizeof(uint32_t)); if (n == 0) return AQS_OK;
+    uint64_t* idx = (uint64_t*)malloc(sizeof(uint64_t) * n);
+    if (orc_sample(s->a, s->n, u, n, idx, 0)) { free(idx); return fail(AQS_ERR_NOMEM, "sample"); }
+    for (uint64_t i = 0; i < n; ++i) hist[idx[i]]++;
+    free(idx); return AQS_OK;
+}
+
+int aqs_timer_create(aqs_timer_t* out) { REQ(out, "null"); *out = (aqs_timer_t)calloc(1, sizeof **out); return AQS_OK; }
+int aqs_timer_start(aqs_timer_t t, aqs_state_t s) { (void)s; clock_gettime(CLOCK_MONOTONIC, &t->a); return AQS_OK; }
+int aqs_timer_stop(aqs_timer_t t, aqs_state_t s) { (void)s; clock_gettime(CLOCK_MONOTONIC, &t->b); return AQS_OK; }
+int aqs_timer_elapsed_ms(aqs_timer_t t, double* ms) { *ms = (t->b.tv_sec - t->a.tv_sec) * 1e3 + (t->b.tv_nsec - t->a.tv_nsec) * 1e-6; return AQS_OK; }
+int aqs_timer_destroy(aqs_timer_t t) { free(t); return AQS_OK; }
+int aqs_counters_get(aqs_counters* out) { REQ(out, "null"); *out = g_cnt; return AQS_OK; }
+int aqs_counters_reset(void) { memset(&g_cnt, 0, sizeof g_cnt); return AQS_OK; }

@@ -438,3 +438,51 @@ double orc_rel_l2(const c32* a, const c32* b, uint64_t count) {
     }
     return den > 0 ? sqrt(num / den) : sqrt(num);
 }
+
+/* ---------------------------------------------------------------------------
+ * One engine primitive (include/aqs_engine.h, struct aqs_op) in bit-position
+ * space, with arbitrary control VALUES.  Used by oracle/abi_shim.c, the CPU
+ * stand-in for libaqs_engine.so that lets the C++ host layer be tested in a
+ * GPU-less container.  kind: 0 U2, 1 DIAG, 2 X, 3 SWAP.
+ * ------------------------------------------------------------------------- */
+int orc_apply_prim(c32* a, int n, int kind, int p, int p2, uint64_t cmask, uint64_t cval, const c32* m) {
+    const uint64_t N = 1ULL << n, tm = 1ULL << p;
+    if (kind == 0 || kind == 2) {
+        const c32 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma omp parallel for schedule(static)
+        for (int64_t j = 0; j < (int64_t)(N >> 1); ++j) {
+            uint64_t r0 = ins0((uint64_t)j, p);
+            if ((r0 & cmask) != cval) continue;
+            uint64_t r1 = r0 | tm;
+            c32 x = a[r0], y = a[r1];
+            if (kind == 2) { a[r0] = y; a[r1] = x; }
+            else { a[r0] = cadd(cmul(m00, x), cmul(m01, y)); a[r1] = cadd(cmul(m10, x), cmul(m11, y)); }
+        }
+        return 0;
+    }
+    if (kind == 1) {
+        const c32 d0 = m[0], d1 = m[3];
+        const int d0_one = (d0.re == 1.f && d0.im == 0.f);
+#pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < (int64_t)N; ++r) {
+            if (((uint64_t)r & cmask) != cval) continue;
+            if ((uint64_t)r & tm) a[r] = cmul(d1, a[r]);
+            else if (!d0_one) a[r] = cmul(d0, a[r]);
+        }
+        return 0;
+    }
+    if (kind == 3) {
+        const uint64_t mb = 1ULL << p2;
+#pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < (int64_t)N; ++r) {
+            uint64_t u = (uint64_t)r;
+            if ((u & cmask) != cval) continue;
+            if ((u & tm) && !(u & mb)) {
+                uint64_t v = (u ^ tm) | mb;
+                c32 t = a[u]; a[u] = a[v]; a[v] = t;
+            }
+        }
+        return 0;
+    }
+    return -1;
+}

@@ -135,13 +135,17 @@ def qstate(z: complex, o: complex) -> Tuple[np.complex64, np.complex64]:
     """QState(z, o): normalise in f32 (src/quantum.cpp:145-157)."""
     z = np.complex64(z); o = np.complex64(o)
     f = np.float32
-    mag2 = f(f(f(z.real) * f(z.real)) + f(f(z.imag) * f(z.imag))) + f(f(f(o.real) * f(o.real)) + f(f(o.imag) * f(o.imag)))
-    mag2 = f(mag2)
+    # ((zr*zr + zi*zi) + or*or) + oi*oi, every step rounded to f32, as the C++ evaluates it
+    mag2 = f(f(f(f(z.real) * f(z.real)) + f(f(z.imag) * f(z.imag))) + f(f(o.real) * f(o.real)))
+    mag2 = f(mag2 + f(f(o.imag) * f(o.imag)))
     if mag2 == 0:
         raise ValueError("Cannot normalize a null state")
     mag = f(np.sqrt(mag2))
-    return (np.complex64(complex(f(z.real) / mag, f(z.imag) / mag)),
-            np.complex64(complex(f(o.real) / mag, f(o.imag) / mag)))
+    den = f(mag * mag)   # af::cfloat / float promotes the divisor to complex: x*c/(c*c) (tests.cpp:986-1002 pins it)
+
+    def div(x):
+        return f(f(f(x) * mag) / den)
+    return (np.complex64(complex(div(z.real), div(z.imag))), np.complex64(complex(div(o.real), div(o.imag))))
 
 
 def apply_gate(a: np.ndarray, n: int, gate: tuple, offset: int = 0, xctrl: int = 0, mode: str = "flatten") -> None:

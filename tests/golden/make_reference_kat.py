@@ -101,7 +101,7 @@ state_equiv = [
          expect_init=[ZERO, ZERO, ONE, ZERO], tol=0.0),
     dict(name="CH-active", source="test/tests.cpp:986-1002", n=4,
          init=[ONE, ZERO, ONE, ONE], circuit=[["CH", 0, 1], ["CH", 3, 2]],
-         expect_init=[ONE, [[RS2, 0.0], [RS2, 0.0]], [[RS2, 0.0], [-RS2, 0.0]], ONE], tol=1e-6),
+         expect_init=[ONE, [[RS2, 0.0], [RS2, 0.0]], [[RS2, 0.0], [-RS2, 0.0]], ONE], tol=0.0),
 ]
 
 # --- composite equivalences, compared as whole circuit matrices ------------
