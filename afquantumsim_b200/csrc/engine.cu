@@ -37,6 +37,7 @@ int fail_cuda(cudaError_t e, const char* what, int line) {
 }
 void count_launch(uint64_t n) { c_launches.fetch_add(n, std::memory_order_relaxed); }
 void count_ops(uint64_t n) { c_ops.fetch_add(n, std::memory_order_relaxed); }
+void count_h2d(uint64_t b) { c_h2d.fetch_add(b, std::memory_order_relaxed); }
 int sm_count() { return g_sm_count; }
 
 #define CUDA_TRY(x)                                                           \

@@ -36,6 +36,7 @@ int fail(int code, const std::string& msg);
 int fail_cuda(cudaError_t e, const char* what, int line);
 void count_launch(uint64_t n);
 void count_ops(uint64_t n);
+void count_h2d(uint64_t bytes);
 int sm_count();
 
 int canonicalize(int n, const aqs_op& op, CanonOp& out);
