@@ -20,8 +20,11 @@
 // is indexed by the plain local index, so lanes always touch 32 consecutive
 // 8-byte words: conflict-free for any split.
 //
-// The op list is interpreted at run time (uniform control flow; the only
-// divergence is a control bit that lives on a lane).
+// The op list is interpreted at run time.  Everything that depends only on the
+// op and the segment (which register pairs a control enables, which registers
+// see the target bit set, the structure of the 2x2) is precomputed by the
+// planner into bit masks, so the inner loops are the FP32 work plus one uniform
+// bit test; the only divergence is a control that lives on a lane.
 #pragma once
 #include "common.cuh"
 
@@ -33,26 +36,32 @@ constexpr int kRegs = 1 << kRegBits;     // amplitudes per thread
 constexpr int kMaxTileBits = 12;         // 4096 amplitudes = 32 KiB of shared memory
 constexpr int kMinTileBits = kLaneBits + kRegBits;
 
-enum TileMode : uint8_t { TM_REG_U2 = 0, TM_REG_PERM = 1, TM_LANE_U2 = 2, TM_LANE_PERM = 3, TM_DIAG = 4 };
-enum DiagTarget : uint8_t { DT_THREAD = 4, DT_CTA = 5 };   // 0..3: register bit
+// op modes (TileOp::mode)
+enum TileMode : uint8_t {
+    TM_REG_GEN = 0,    // general complex 2x2 on a register bit
+    TM_REG_REAL = 1,   // all four entries real            (RotY, H)
+    TM_REG_XLIKE = 2,  // m00,m11 real; m01,m10 imaginary  (RotX)
+    TM_REG_PERM = 3,   // bit flip                         (X, CX, CCNot, ...)
+    TM_LANE_GEN = 4,   // general 2x2 on a lane bit
+    TM_LANE_PERM = 5,  // bit flip on a lane bit
+    TM_PHASE = 6       // one factor on the selected amplitudes: every diagonal gate is lowered to these
+                       // (Z, Phase, CZ, CPhase directly; diag(d0,d1) as d0 on the pass scale or as two phases)
+};
 
 struct alignas(16) TileOp {
     uint8_t mode;
-    uint8_t tk;         // REG_*: register bit 0..3; LANE_*: lane bit 0..4; DIAG: 0..3 | DT_THREAD | DT_CTA
-    uint8_t rk_mask;    // control predicate in register-index space: (k & rk_mask) == rk_val
-    uint8_t rk_val;
-    uint16_t tl_mask;   // control predicate on the thread's local index (lane + warp bits)
+    uint8_t tk;          // REG_*: register bit 0..3; LANE_*: lane bit 0..4
+    uint16_t amp_mask;   // REG_*: bit p = pair p enabled (8 bits); others: bit k = register k enabled
+    uint16_t pad2;
+    uint16_t tl_mask;    // control predicate on the thread's local index (lane + warp bits): (base & tl_mask) == tl_val
     uint16_t tl_val;
-    uint16_t tl_tbit;   // DIAG / DT_THREAD: local-index mask of the target bit
-    uint8_t d0_one;     // DIAG: m[0] == 1
-    uint8_t pad;
-    uint32_t pad2;
-    uint64_t g_mask;    // control predicate on the tile's global base index (bits outside the tile)
+    uint16_t pad0;
+    uint32_t pad1;
+    uint64_t g_mask;     // control predicate on the tile's global base index (bits outside the tile)
     uint64_t g_val;
-    uint64_t g_tbit;    // DIAG / DT_CTA: global mask of the target bit
-    float2 m[4];
+    float2 m[4];         // 2x2 row-major; PHASE uses m[0]
 };
-static_assert(sizeof(TileOp) == 80, "TileOp layout");
+static_assert(sizeof(TileOp) == 64, "TileOp layout");
 
 struct TileSeg {
     uint8_t R[kRegBits];   // local positions of the register bits (each >= 5)
@@ -68,40 +77,48 @@ struct TileArgs {
     const TileOp* ops;
     uint32_t n_segs;
     uint32_t tile_bits;    // T
+    float2 scale;          // global factor of the pass (product of the phases folded out of RotZ-like ops)
+    uint32_t has_scale;
     BitList tile;          // global positions of the tile bits, ascending (tile.pos[0..4] = 0..4)
 };
 
-template <int TK, bool PERM>
-__device__ __forceinline__ void reg_pairs(float2 (&a)[kRegs], const TileOp& op, bool thr_ok) {
-    const float2 m00 = op.m[0], m01 = op.m[1], m10 = op.m[2], m11 = op.m[3];
+template <int TK, int MODE>
+__device__ __forceinline__ void reg_pairs(float2 (&a)[kRegs], const float2 (&m)[4], uint32_t pair_mask) {
 #pragma unroll
     for (int p = 0; p < kRegs / 2; ++p) {
         const int k0 = ((p >> TK) << (TK + 1)) | (p & ((1 << TK) - 1));
         const int k1 = k0 | (1 << TK);
-        if (thr_ok && ((k0 & op.rk_mask) == op.rk_val)) {
+        if (pair_mask >> p & 1u) {
             const float2 x = a[k0], y = a[k1];
-            if (PERM) {
+            if (MODE == TM_REG_PERM) {
                 a[k0] = y; a[k1] = x;
+            } else if (MODE == TM_REG_REAL) {
+                a[k0] = make_float2(fmaf(m[1].x, y.x, m[0].x * x.x), fmaf(m[1].x, y.y, m[0].x * x.y));
+                a[k1] = make_float2(fmaf(m[3].x, y.x, m[2].x * x.x), fmaf(m[3].x, y.y, m[2].x * x.y));
+            } else if (MODE == TM_REG_XLIKE) {
+                // (r + i s)(yr + i yi) with r = 0: i*s*y = (-s*yi, s*yr)
+                a[k0] = make_float2(fmaf(-m[1].y, y.y, m[0].x * x.x), fmaf(m[1].y, y.x, m[0].x * x.y));
+                a[k1] = make_float2(fmaf(-m[2].y, x.y, m[3].x * y.x), fmaf(m[2].y, x.x, m[3].x * y.y));
             } else {
-                a[k0] = cdot2(m00, x, m01, y);
-                a[k1] = cdot2(m10, x, m11, y);
+                a[k0] = cdot2(m[0], x, m[1], y);
+                a[k1] = cdot2(m[2], x, m[3], y);
             }
         }
     }
 }
 
-template <bool PERM>
-__device__ __forceinline__ void reg_dispatch(float2 (&a)[kRegs], const TileOp& op, bool thr_ok) {
-    switch (op.tk) {
-        case 0: reg_pairs<0, PERM>(a, op, thr_ok); break;
-        case 1: reg_pairs<1, PERM>(a, op, thr_ok); break;
-        case 2: reg_pairs<2, PERM>(a, op, thr_ok); break;
-        default: reg_pairs<3, PERM>(a, op, thr_ok); break;
+template <int MODE>
+__device__ __forceinline__ void reg_dispatch(float2 (&a)[kRegs], const float2 (&m)[4], uint32_t tk, uint32_t pair_mask) {
+    switch (tk) {
+        case 0: reg_pairs<0, MODE>(a, m, pair_mask); break;
+        case 1: reg_pairs<1, MODE>(a, m, pair_mask); break;
+        case 2: reg_pairs<2, MODE>(a, m, pair_mask); break;
+        default: reg_pairs<3, MODE>(a, m, pair_mask); break;
     }
 }
 
 template <int WARPS_LOG2>
-__global__ void __launch_bounds__(32 << WARPS_LOG2, (WARPS_LOG2 == 3 ? 3 : 4)) k_tile(const __grid_constant__ TileArgs P) {
+__global__ void __launch_bounds__(32 << WARPS_LOG2, 4) k_tile(const __grid_constant__ TileArgs P) {
     constexpr int T = kMinTileBits + WARPS_LOG2;
     __shared__ float2 sm[1 << T];
 
@@ -127,7 +144,6 @@ __global__ void __launch_bounds__(32 << WARPS_LOG2, (WARPS_LOG2 == 3 ? 3 : 4)) k
             if (k >> i & 1) x |= roff[i];
         return x;
     };
-    // global address pieces of the current split
     auto spread_thread = [&]() {
         uint64_t g = gbase | (uint64_t)lane;   // tile.pos[0..4] == 0..4
         for (int j = kLaneBits; j < T; ++j)
@@ -166,57 +182,58 @@ __global__ void __launch_bounds__(32 << WARPS_LOG2, (WARPS_LOG2 == 3 ? 3 : 4)) k
         }
         const uint32_t end = sg.first_op + sg.n_ops;
         for (uint32_t o = sg.first_op; o < end; ++o) {
-            const TileOp& op = P.ops[o];
-            if ((gbase & op.g_mask) != op.g_val) continue;              // CTA-uniform control outside the tile
-            const bool thr_ok = ((base_local & op.tl_mask) == op.tl_val);
-            switch (op.mode) {
-                case TM_REG_U2: reg_dispatch<false>(a, op, thr_ok); break;
-                case TM_REG_PERM: reg_dispatch<true>(a, op, thr_ok); break;
-                case TM_LANE_U2: {
-                    const uint32_t xm = 1u << op.tk;
-                    const bool hi = (lane & xm) != 0;
-                    const float2 mx = hi ? op.m[2] : op.m[0];
-                    const float2 my = hi ? op.m[3] : op.m[1];
+            const TileOp* op = P.ops + o;
+            const ulonglong2 gm = *reinterpret_cast<const ulonglong2*>(&op->g_mask);
+            if ((gbase & gm.x) != gm.y) continue;                       // CTA-uniform control outside the tile
+            const uint4 hd = *reinterpret_cast<const uint4*>(op);       // mode,tk,amp_mask | -,tl_mask | tl_val,..
+            const uint32_t mode = hd.x & 0xffu, tk = (hd.x >> 8) & 0xffu, amp_mask = hd.x >> 16;
+            const uint32_t tl_mask = hd.y >> 16, tl_val = hd.z & 0xffffu;
+            const bool thr_ok = ((base_local & tl_mask) == tl_val);
+            float2 m[4];
+            {
+                const float4 m01 = *reinterpret_cast<const float4*>(&op->m[0]);
+                const float4 m23 = *reinterpret_cast<const float4*>(&op->m[2]);
+                m[0] = make_float2(m01.x, m01.y); m[1] = make_float2(m01.z, m01.w);
+                m[2] = make_float2(m23.x, m23.y); m[3] = make_float2(m23.z, m23.w);
+            }
+            if (mode <= TM_REG_PERM) {
+                if (thr_ok) {
+                    switch (mode) {
+                        case TM_REG_GEN: reg_dispatch<TM_REG_GEN>(a, m, tk, amp_mask); break;
+                        case TM_REG_REAL: reg_dispatch<TM_REG_REAL>(a, m, tk, amp_mask); break;
+                        case TM_REG_XLIKE: reg_dispatch<TM_REG_XLIKE>(a, m, tk, amp_mask); break;
+                        default: reg_dispatch<TM_REG_PERM>(a, m, tk, amp_mask); break;
+                    }
+                }
+            } else if (mode == TM_PHASE) {
+                if (thr_ok) {
+#pragma unroll
+                    for (int k = 0; k < kRegs; ++k)
+                        if (amp_mask >> k & 1u) a[k] = cmul(m[0], a[k]);
+                }
+            } else {
+                // lane-bit target: every lane takes part in the shuffles; thr_ok only gates the update
+                const uint32_t xm = 1u << tk;
+                const bool hi = (lane & xm) != 0;
+                const uint32_t act = thr_ok ? amp_mask : 0u;
+                if (mode == TM_LANE_GEN) {
+                    const float2 m_own = hi ? m[3] : m[0];
+                    const float2 m_oth = hi ? m[2] : m[1];
 #pragma unroll
                     for (int k = 0; k < kRegs; ++k) {
                         float2 other;
                         other.x = __shfl_xor_sync(0xffffffffu, a[k].x, xm);
                         other.y = __shfl_xor_sync(0xffffffffu, a[k].y, xm);
-                        if (thr_ok && ((k & op.rk_mask) == op.rk_val)) {
-                            const float2 x = hi ? other : a[k];
-                            const float2 y = hi ? a[k] : other;
-                            a[k] = cdot2(mx, x, my, y);
-                        }
+                        if (act >> k & 1u) a[k] = cdot2(m_own, a[k], m_oth, other);
                     }
-                    break;
-                }
-                case TM_LANE_PERM: {
-                    const uint32_t xm = 1u << op.tk;
+                } else {
 #pragma unroll
                     for (int k = 0; k < kRegs; ++k) {
                         float2 other;
                         other.x = __shfl_xor_sync(0xffffffffu, a[k].x, xm);
                         other.y = __shfl_xor_sync(0xffffffffu, a[k].y, xm);
-                        if (thr_ok && ((k & op.rk_mask) == op.rk_val)) a[k] = other;
+                        if (act >> k & 1u) a[k] = other;
                     }
-                    break;
-                }
-                default: {   // TM_DIAG
-                    const float2 d0 = op.m[0], d1 = op.m[3];
-                    bool tbit = false;
-                    if (op.tk == DT_THREAD) tbit = (base_local & op.tl_tbit) != 0;
-                    else if (op.tk == DT_CTA) tbit = (gbase & op.g_tbit) != 0;
-                    if (thr_ok) {
-#pragma unroll
-                        for (int k = 0; k < kRegs; ++k) {
-                            if ((k & op.rk_mask) == op.rk_val) {
-                                const bool bit = op.tk < kRegBits ? ((k >> op.tk) & 1) != 0 : tbit;
-                                if (bit) a[k] = cmul(d1, a[k]);
-                                else if (!op.d0_one) a[k] = cmul(d0, a[k]);
-                            }
-                        }
-                    }
-                    break;
                 }
             }
         }
@@ -227,13 +244,15 @@ __global__ void __launch_bounds__(32 << WARPS_LOG2, (WARPS_LOG2 == 3 ? 3 : 4)) k
         uint64_t go[kRegBits];
 #pragma unroll
         for (int i = 0; i < kRegBits; ++i) go[i] = 1ull << P.tile.pos[sg.R[i]];
+        const bool sc = P.has_scale != 0;
+        const float2 f = P.scale;
 #pragma unroll
         for (int k = 0; k < kRegs; ++k) {
             uint64_t g = gt;
 #pragma unroll
             for (int i = 0; i < kRegBits; ++i)
                 if (k >> i & 1) g |= go[i];
-            P.state[g] = a[k];
+            P.state[g] = sc ? cmul(f, a[k]) : a[k];
         }
     }
 }

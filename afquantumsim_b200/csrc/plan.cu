@@ -15,6 +15,7 @@
 // Diagonal ops and controls never constrain the tile: QFT's CPhase ladder fuses freely.
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -178,6 +179,7 @@ static int build_fused(aqs_plan_s* p) {
         for (int b = 0; b < n && popc(tile) < T; ++b) tile |= 1ull << b;
 
         FusedPass fp;
+        std::complex<double> pass_scale(1.0, 0.0);
         fp.warps_log2 = T - kMinTileBits;
         fp.n_tiles = 1ull << (n - T);
         std::memset(&fp.args, 0, sizeof fp.args);
@@ -213,56 +215,88 @@ static int build_fused(aqs_plan_s* p) {
                 else sg.W[wi++] = (uint8_t)j;
             }
             sg.first_op = (uint32_t)fp.ops.size();
-            for (int idx : seg_taken) {
-                const CanonOp& c = ops[idx];
+            // emits one tile op; (cm, cv) are the complete control mask/value in global bit positions
+            auto emit = [&](const CanonOp& c, uint8_t mode, int tk, uint64_t cm, uint64_t cv, const float2 m[4]) {
                 TileOp t;
                 std::memset(&t, 0, sizeof t);
-                for (int i = 0; i < 4; ++i) t.m[i] = c.m[i];
-                // controls
-                uint64_t cm = c.cmask, cv = c.cval;
-                bool uniform_phase = false;
-                if (c.kind == AQS_OP_DIAG && c.d0_one) {   // phase on a subset: fold the target into the controls
-                    cm |= 1ull << c.p; cv |= 1ull << c.p;
-                    uniform_phase = true;
-                }
+                t.mode = mode;
+                t.tk = (uint8_t)tk;
+                for (int i = 0; i < 4; ++i) t.m[i] = m[i];
                 t.g_mask = cm & ~tile;
                 t.g_val = cv & ~tile;
+                uint32_t rk_mask = 0, rk_val = 0;
                 for (int b = 0; b < n; ++b) {
                     if (!(cm & tile & (1ull << b))) continue;
                     const int j = local_of_bit[b];
                     const uint32_t v = (cv >> b) & 1ull;
                     if (reg_index_of_local[j] >= 0) {
-                        t.rk_mask |= (uint8_t)(1u << reg_index_of_local[j]);
-                        t.rk_val |= (uint8_t)(v << reg_index_of_local[j]);
+                        rk_mask |= 1u << reg_index_of_local[j];
+                        rk_val |= v << reg_index_of_local[j];
                     } else {
                         t.tl_mask |= (uint16_t)(1u << j);
                         t.tl_val |= (uint16_t)(v << j);
                     }
                 }
-                if (c.kind == AQS_OP_DIAG) {
-                    t.mode = TM_DIAG;
-                    if (uniform_phase) {
-                        t.tk = DT_CTA; t.g_tbit = 0;       // target bit reads 0 => every selected amplitude gets m[0]
-                        t.m[0] = c.m[3]; t.d0_one = 0;
-                    } else {
-                        t.d0_one = 0;
-                        const int j = local_of_bit[c.p];
-                        if (j < 0) { t.tk = DT_CTA; t.g_tbit = 1ull << c.p; }
-                        else if (reg_index_of_local[j] >= 0) t.tk = (uint8_t)reg_index_of_local[j];
-                        else { t.tk = DT_THREAD; t.tl_tbit = (uint16_t)(1u << j); }
+                uint32_t act = 0;   // registers enabled by the controls that live on register bits
+                for (uint32_t k = 0; k < (uint32_t)kRegs; ++k)
+                    if ((k & rk_mask) == rk_val) act |= 1u << k;
+                if (mode <= TM_REG_PERM) {
+                    uint32_t pairs = 0;
+                    for (int pr = 0; pr < kRegs / 2; ++pr) {
+                        const int k0 = ((pr >> tk) << (tk + 1)) | (pr & ((1 << tk) - 1));
+                        if (act >> k0 & 1u) pairs |= 1u << pr;
                     }
+                    t.amp_mask = (uint16_t)pairs;
                 } else {
-                    const int j = local_of_bit[c.p];
-                    const bool perm = (c.kind == AQS_OP_X);
-                    if (j < kLaneBits) { t.mode = perm ? TM_LANE_PERM : TM_LANE_U2; t.tk = (uint8_t)j; }
-                    else { t.mode = perm ? TM_REG_PERM : TM_REG_U2; t.tk = (uint8_t)reg_index_of_local[j]; }
+                    t.amp_mask = (uint16_t)act;
                 }
+                (void)c;
                 fp.ops.push_back(t);
+            };
+            for (int idx : seg_taken) {
+                const CanonOp& c = ops[idx];
+                if (c.kind == AQS_OP_DIAG) {
+                    // every diagonal becomes "one factor on a selected subset"
+                    const uint64_t tb = 1ull << c.p;
+                    float2 one[4] = {make_float2(1.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(1.f, 0.f)};
+                    if (c.d0_one) {
+                        one[0] = c.m[3];
+                        emit(c, TM_PHASE, 0, c.cmask | tb, c.cval | tb, one);
+                    } else if (c.cmask == 0) {
+                        // diag(d0, d1) = d0 * diag(1, d1/d0): d0 goes to the pass-wide scale
+                        const std::complex<double> d0(c.m[0].x, c.m[0].y), d1(c.m[3].x, c.m[3].y);
+                        pass_scale *= d0;
+                        const std::complex<double> r = d1 / d0;
+                        one[0] = make_float2((float)r.real(), (float)r.imag());
+                        emit(c, TM_PHASE, 0, tb, tb, one);
+                    } else {
+                        one[0] = c.m[0];
+                        emit(c, TM_PHASE, 0, c.cmask | tb, c.cval, one);        // target bit 0
+                        one[0] = c.m[3];
+                        emit(c, TM_PHASE, 0, c.cmask | tb, c.cval | tb, one);   // target bit 1
+                    }
+                    continue;
+                }
+                const int j = local_of_bit[c.p];
+                const bool perm = (c.kind == AQS_OP_X);
+                float2 m[4];
+                full_matrix(c, m);
+                if (j < kLaneBits) {
+                    emit(c, perm ? TM_LANE_PERM : TM_LANE_GEN, j, c.cmask, c.cval, m);
+                } else {
+                    uint8_t mode = TM_REG_GEN;
+                    if (perm) mode = TM_REG_PERM;
+                    else if (m[0].y == 0.f && m[1].y == 0.f && m[2].y == 0.f && m[3].y == 0.f) mode = TM_REG_REAL;
+                    else if (m[0].y == 0.f && m[3].y == 0.f && m[1].x == 0.f && m[2].x == 0.f) mode = TM_REG_XLIKE;
+                    emit(c, mode, reg_index_of_local[j], c.cmask, c.cval, m);
+                }
             }
             sg.n_ops = (uint32_t)fp.ops.size() - sg.first_op;
             fp.segs.push_back(sg);
             seg_cand.swap(seg_rest);
         }
+        fp.args.scale = make_float2((float)pass_scale.real(), (float)pass_scale.imag());
+        fp.args.has_scale = (pass_scale != std::complex<double>(1.0, 0.0)) ? 1u : 0u;
         p->passes.push_back(std::move(fp));
         cand.swap(rest);
     }
