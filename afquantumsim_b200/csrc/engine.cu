@@ -256,11 +256,30 @@ int aqs_state_create(int n, aqs_state_t* out) {
     return aqs_state_set_basis(s, 0);
 }
 
+int aqs_state_wrap(int n, void* device_ptr, aqs_state_t* out) {
+    REQUIRE_INIT();
+    REQUIRE(out != nullptr && device_ptr != nullptr, "null argument");
+    REQUIRE(n >= 1 && n <= AQS_MAX_QUBITS, "qubit count must be in [1, AQS_MAX_QUBITS]");
+    REQUIRE(((uintptr_t)device_ptr & 15u) == 0, "device pointer must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(g_device));
+    aqs_state_s* s = new (std::nothrow) aqs_state_s();
+    if (!s) return fail(AQS_ERR_NOMEM, "host allocation failed");
+    s->n = n;
+    s->N = 1ull << n;
+    s->d = (float2*)device_ptr;
+    s->own_memory = false;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return fail_cuda(e, "cudaStreamCreate", __LINE__); }
+    s->own_stream = true;
+    *out = s;
+    return AQS_OK;
+}
+
 int aqs_state_destroy(aqs_state_t s) {
     if (!s) return AQS_OK;
     cudaStreamSynchronize(s->stream);
     if (s->scratch) cudaFree(s->scratch);
-    if (s->d) cudaFree(s->d);
+    if (s->d && s->own_memory) cudaFree(s->d);
     if (s->own_stream) cudaStreamDestroy(s->stream);
     delete s;
     return AQS_OK;
@@ -473,15 +492,16 @@ int aqs_collapse_qubit(aqs_state_t s, int qubit, int outcome, float p) {
     return AQS_OK;
 }
 
-static int sample_impl(aqs_state_t s, const float* u_host, uint64_t n_draws, uint64_t* out_host, uint32_t* hist_host) {
+static int sample_impl(aqs_state_t s, const float* u_host, const uint64_t* ufix_host, uint64_t n_draws, uint64_t* out_host,
+                       uint32_t* hist_host) {
     REQUIRE_INIT();
-    REQUIRE(s && (u_host || n_draws == 0), "null argument");
+    REQUIRE(s && (u_host || ufix_host || n_draws == 0), "null argument");
     REQUIRE(n_draws <= 0x7fffffffull, "too many draws for one call");
     const uint64_t tile_amps = std::min<uint64_t>(s->N, kTileAmps);
     const uint64_t n_tiles = s->N / tile_amps;
-    // scratch layout: [tile sums: n_tiles u64][u: n_draws f32 (padded)][out: n_draws u64]
+    // scratch layout: [tile sums: n_tiles u64][u: n_draws f32 or u64 (padded)][out: n_draws u64]
     const size_t off_u = ((n_tiles * 8 + 255) / 256) * 256;
-    const size_t off_o = off_u + ((n_draws * 4 + 255) / 256) * 256;
+    const size_t off_o = off_u + ((n_draws * 8 + 255) / 256) * 256;
     const size_t need = off_o + n_draws * 8 + 256;
     int rc = ensure_scratch(s, need);
     if (rc) return rc;
@@ -500,10 +520,13 @@ static int sample_impl(aqs_state_t s, const float* u_host, uint64_t n_draws, uin
     count_launch(2);
     cudaError_t e = cudaSuccess;
     if (n_draws) {
-        e = cudaMemcpyAsync(u_dev, u_host, n_draws * 4, cudaMemcpyHostToDevice, s->stream);
-        c_h2d += n_draws * 4;
+        const size_t ub = ufix_host ? 8 : 4;
+        e = cudaMemcpyAsync(u_dev, ufix_host ? (const void*)ufix_host : (const void*)u_host, n_draws * ub,
+                            cudaMemcpyHostToDevice, s->stream);
+        c_h2d += n_draws * ub;
         if (e == cudaSuccess) {
-            k_sample<<<(unsigned)n_draws, 256, 0, s->stream>>>(s->d, tile_amps, n_tiles, sums, u_dev,
+            k_sample<<<(unsigned)n_draws, 256, 0, s->stream>>>(s->d, tile_amps, n_tiles, sums, ufix_host ? nullptr : u_dev,
+                                                              ufix_host ? (const unsigned long long*)u_dev : nullptr,
                                                               out_host ? out_dev : nullptr, hist_dev);
             count_launch(1);
             e = cudaGetLastError();
@@ -525,11 +548,15 @@ static int sample_impl(aqs_state_t s, const float* u_host, uint64_t n_draws, uin
 
 int aqs_sample(aqs_state_t s, const float* u, uint64_t n, uint64_t* out) {
     REQUIRE(out || n == 0, "null output");
-    return sample_impl(s, u, n, out, nullptr);
+    return sample_impl(s, u, nullptr, n, out, nullptr);
+}
+int aqs_sample_fixed(aqs_state_t s, const uint64_t* u, uint64_t n, uint64_t* out) {
+    REQUIRE((out && u) || n == 0, "null argument");
+    return sample_impl(s, nullptr, u, n, out, nullptr);
 }
 int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     REQUIRE(hist, "null histogram");
-    return sample_impl(s, u, n, nullptr, hist);
+    return sample_impl(s, u, nullptr, n, nullptr, hist);
 }
 
 // ---- timers -------------------------------------------------------------------------

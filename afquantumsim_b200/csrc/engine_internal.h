@@ -14,6 +14,7 @@ struct aqs_state_s {
     float2* d = nullptr;          // 2^n complex64, interleaved, in HBM
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool own_memory = true;       // false for aqs_state_wrap (caller-owned allocation)
     void* scratch = nullptr;      // reductions / sampling workspace
     size_t scratch_bytes = 0;
 };

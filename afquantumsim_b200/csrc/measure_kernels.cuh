@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(unsigned long long* s, uint
 // out = min{ k : S_k > U }, or 0 when U >= total (peek_measure_all :353-356).
 __global__ void __launch_bounds__(256) k_sample(const float2* __restrict__ a, uint64_t tile_amps, uint64_t n_tiles,
                                                 const unsigned long long* __restrict__ incl,
-                                                const float* __restrict__ u, unsigned long long* __restrict__ out,
-                                                uint32_t* __restrict__ hist) {
+                                                const float* __restrict__ u, const unsigned long long* __restrict__ u_fixed,
+                                                unsigned long long* __restrict__ out, uint32_t* __restrict__ hist) {
     const uint64_t d = blockIdx.x;
-    const unsigned long long U = fix62(u[d]);
+    const unsigned long long U = u_fixed ? u_fixed[d] : fix62(u[d]);
     // first tile t with incl[t] > U  (every thread runs the same uniform search)
     uint64_t lo = 0, hi = n_tiles;
     while (lo < hi) {
@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256) k_sample(const float2* __restrict__ a, ui
         if (incl[mid] > U) hi = mid; else lo = mid + 1;
     }
     if (lo == n_tiles) {
-        if (threadIdx.x == 0) { if (out) out[d] = 0ull; if (hist) atomicAdd(&hist[0], 1u); }
+        // no index qualifies: 0 for the public rule (peek_measure_all), "not in this shard" for the fixed-point entry
+        if (threadIdx.x == 0) { if (out) out[d] = u_fixed ? ~0ull : 0ull; if (hist) atomicAdd(&hist[0], 1u); }
         return;
     }
     const uint64_t t = lo;

@@ -49,12 +49,12 @@ _inited = False
 # every symbol include/aqs_engine.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "aqs_engine_init", "aqs_engine_shutdown", "aqs_engine_device", "aqs_engine_abi_version", "aqs_last_error",
-    "aqs_state_create", "aqs_state_destroy", "aqs_state_clone", "aqs_state_qubits", "aqs_state_set_basis",
+    "aqs_state_create", "aqs_state_wrap", "aqs_state_destroy", "aqs_state_clone", "aqs_state_qubits", "aqs_state_set_basis",
     "aqs_state_set_product", "aqs_state_set_identity", "aqs_state_upload", "aqs_state_download",
     "aqs_state_get_amp", "aqs_state_device_ptr", "aqs_state_set_stream", "aqs_state_get_stream", "aqs_sync",
     "aqs_apply_op", "aqs_apply_ops", "aqs_plan_build", "aqs_plan_run", "aqs_plan_get_info", "aqs_plan_destroy",
     "aqs_norm2", "aqs_scale", "aqs_prob_fixed", "aqs_qubit_prob1", "aqs_probabilities", "aqs_collapse_qubit",
-    "aqs_sample", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
+    "aqs_sample", "aqs_sample_fixed", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
 ]
 
@@ -73,7 +73,7 @@ def load():
     sig = {
         "aqs_engine_init": [i32], "aqs_engine_shutdown": [],
         "aqs_engine_device": [P(i32), P(i32), P(ctypes.c_size_t)],
-        "aqs_state_create": [i32, P(vp)], "aqs_state_destroy": [vp], "aqs_state_clone": [vp, P(vp)],
+        "aqs_state_create": [i32, P(vp)], "aqs_state_wrap": [i32, vp, P(vp)], "aqs_state_destroy": [vp], "aqs_state_clone": [vp, P(vp)],
         "aqs_state_qubits": [vp, P(i32)], "aqs_state_set_basis": [vp, u64], "aqs_state_set_product": [vp, vp],
         "aqs_state_set_identity": [vp], "aqs_state_upload": [vp, vp, u64, u64],
         "aqs_state_download": [vp, vp, u64, u64], "aqs_state_get_amp": [vp, u64, vp],
@@ -84,7 +84,7 @@ def load():
         "aqs_norm2": [vp, P(ctypes.c_double)], "aqs_scale": [vp, f32],
         "aqs_prob_fixed": [vp, u64, u64, P(u64)], "aqs_qubit_prob1": [vp, i32, P(ctypes.c_double)],
         "aqs_probabilities": [vp, vp, u64, u64], "aqs_collapse_qubit": [vp, i32, i32, f32],
-        "aqs_sample": [vp, vp, u64, vp], "aqs_sample_hist": [vp, vp, u64, vp],
+        "aqs_sample": [vp, vp, u64, vp], "aqs_sample_fixed": [vp, vp, u64, vp], "aqs_sample_hist": [vp, vp, u64, vp],
         "aqs_timer_create": [P(vp)], "aqs_timer_start": [vp, vp], "aqs_timer_stop": [vp, vp],
         "aqs_timer_elapsed_ms": [vp, P(ctypes.c_double)], "aqs_timer_destroy": [vp],
         "aqs_counters_get": [P(Counters)], "aqs_counters_reset": [],
@@ -226,6 +226,14 @@ class State:
             self._h = ctypes.c_void_p()
             _check(load().aqs_state_create(n_qubits, ctypes.byref(self._h)))
 
+    @classmethod
+    def wrap(cls, n_qubits: int, device_ptr: int) -> "State":
+        """Engine state on caller-owned device memory (e.g. a torch tensor's data_ptr())."""
+        ensure_init()
+        h = ctypes.c_void_p()
+        _check(load().aqs_state_wrap(n_qubits, ctypes.c_void_p(device_ptr), ctypes.byref(h)))
+        return cls(n_qubits, _handle=h)
+
     def close(self):
         if getattr(self, "_h", None):
             load().aqs_state_destroy(self._h)
@@ -321,6 +329,14 @@ class State:
         out = np.empty(u.size, dtype=np.uint64)
         _check(load().aqs_sample(self._h, u.ctypes.data_as(ctypes.c_void_p), u.size,
                                  out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def sample_fixed(self, u_fixed: np.ndarray) -> np.ndarray:
+        """Local indices for fixed-point thresholds (2^-62 units); UINT64_MAX = not in this shard."""
+        u = np.ascontiguousarray(u_fixed, dtype=np.uint64)
+        out = np.empty(u.size, dtype=np.uint64)
+        _check(load().aqs_sample_fixed(self._h, u.ctypes.data_as(ctypes.c_void_p), u.size,
+                                       out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
     def sample_hist(self, u: np.ndarray) -> np.ndarray:

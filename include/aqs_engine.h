@@ -89,6 +89,10 @@ const char* aqs_last_error(void);
  * aqs_state_create: af::constant(0, 2^n, c32) of the QSimulator constructors
  * (src/quantum.cpp:212-218); the state is left at |0...0>.  */
 int aqs_state_create(int n_qubits, aqs_state_t* out);
+/* same, on caller-owned device memory (2^n complex64, 16-byte aligned): the engine
+ * neither allocates nor frees it and leaves its contents untouched.  Lets a host that
+ * owns the allocation (torch tensors for the NCCL half-shard exchanges) run kernels on it. */
+int aqs_state_wrap(int n_qubits, void* device_ptr, aqs_state_t* out);
 int aqs_state_destroy(aqs_state_t s);
 /* copy construction of QSimulator (af::array value semantics; used e.g. by
  * examples/quantum_teleportation.cpp) */
@@ -167,6 +171,10 @@ int aqs_collapse_qubit(aqs_state_t s, int qubit, int outcome, float p);
  * (src/quantum.cpp:344-359, 467-501).  Draws are an INPUT so that results are
  * reproducible; the host layer owns the RNG (src/quantum.cpp:57-62). */
 int aqs_sample(aqs_state_t s, const float* u_host, uint64_t n_draws, uint64_t* out_index_host);
+/* same rule with the draws already in the fixed-point domain (U = trunc(u * 2^62), possibly
+ * minus the probability mass of lower-ranked shards): the sharded sampler's local step.
+ * out = local index of the first S_k > U, or UINT64_MAX if U >= the shard's total. */
+int aqs_sample_fixed(aqs_state_t s, const uint64_t* u_fixed_host, uint64_t n_draws, uint64_t* out_index_host);
 /* same, reduced on the device to the dense histogram profile_measure_all returns
  * (std::vector<uint32_t>(2^n), src/quantum.cpp:470,498); hist_host has 2^n entries */
 int aqs_sample_hist(aqs_state_t s, const float* u_host, uint64_t n_draws, uint32_t* hist_host);

@@ -29,7 +29,8 @@ double orc_norm2(const c32* a, int n);
 void orc_collapse_qubit(c32* a, int n, int qubit, int outcome, float p);
 int orc_sample(const c32* a, int n, const float* u, uint64_t draws, uint64_t* out, int mode);
 
-struct aqs_state_s { int n; uint64_t N; c32* a; };
+struct aqs_state_s { int n; uint64_t N; c32* a; int own; };
+int orc_sample_fixed(const c32* a, int n, const uint64_t* U, uint64_t draws, uint64_t* out);
 struct aqs_plan_s { int n; uint64_t n_ops; aqs_op* ops; double bytes; };
 struct aqs_timer_s { struct timespec a, b; };
 
@@ -55,10 +56,19 @@ int aqs_state_create(int n, aqs_state_t* out) {
     s->a = (c32*)calloc(s->N, sizeof(c32));
     if (!s->a) { free(s); return fail(AQS_ERR_NOMEM, "allocation failed"); }
     s->a[0].re = 1.f;
+    s->own = 1;
     *out = s;
     return AQS_OK;
 }
-int aqs_state_destroy(aqs_state_t s) { if (s) { free(s->a); free(s); } return AQS_OK; }
+int aqs_state_wrap(int n, void* ptr, aqs_state_t* out) {
+    if (!g_init) return fail(AQS_ERR_STATE, "aqs_engine_init has not been called");
+    REQ(out && ptr, "null argument"); REQ(n >= 1 && n <= 30, "qubit count must be in [1, 30] (cpu shim)");
+    aqs_state_t s = (aqs_state_t)calloc(1, sizeof *s);
+    s->n = n; s->N = 1ULL << n; s->a = (c32*)ptr; s->own = 0;
+    *out = s;
+    return AQS_OK;
+}
+int aqs_state_destroy(aqs_state_t s) { if (s) { if (s->own) free(s->a); free(s); } return AQS_OK; }
 int aqs_state_clone(aqs_state_t src, aqs_state_t* out) {
     REQ(src && out, "null handle");
     int rc = aqs_state_create(src->n, out);
@@ -166,6 +176,10 @@ int aqs_collapse_qubit(aqs_state_t s, int q, int outcome, float p) {
 int aqs_sample(aqs_state_t s, const float* u, uint64_t n, uint64_t* out) {
     REQ(s && (out || n == 0), "null"); if (n == 0) return AQS_OK;
     return orc_sample(s->a, s->n, u, n, out, 0) ? fail(AQS_ERR_NOMEM, "sample") : AQS_OK;
+}
+int aqs_sample_fixed(aqs_state_t s, const uint64_t* u, uint64_t n, uint64_t* out) {
+    REQ(s && ((out && u) || n == 0), "null"); if (n == 0) return AQS_OK;
+    return orc_sample_fixed(s->a, s->n, u, n, out) ? fail(AQS_ERR_NOMEM, "sample") : AQS_OK;
 }
 int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     REQ(s && hist, "null"); memset(hist, 0, s->N * sizeof(uint32_t)); if (n == 0) return AQS_OK;

@@ -427,6 +427,23 @@ int orc_sample(const c32* a, int n, const float* u, uint64_t draws, uint64_t* ou
     }
 }
 
+/* Local step of sharded sampling: thresholds already in the fixed-point domain.
+ * out = first local k with S_k > U, or UINT64_MAX when U >= the shard's total. */
+int orc_sample_fixed(const c32* a, int n, const uint64_t* U, uint64_t draws, uint64_t* out) {
+    const uint64_t N = 1ULL << n;
+    uint64_t* S = (uint64_t*)malloc(sizeof(uint64_t) * N);
+    if (!S) return -1;
+    uint64_t s = 0;
+    for (uint64_t r = 0; r < N; ++r) { s += fix62(prob32(a[r])); S[r] = s; }
+    for (uint64_t i = 0; i < draws; ++i) {
+        uint64_t lo = 0, hi = N;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (S[mid] > U[i]) hi = mid; else lo = mid + 1; }
+        out[i] = (lo == N) ? UINT64_MAX : lo;
+    }
+    free(S);
+    return 0;
+}
+
 /* relative L2 distance ||a-b|| / ||b||, in double — used by the parity tests */
 double orc_rel_l2(const c32* a, const c32* b, uint64_t count) {
     double num = 0.0, den = 0.0;

@@ -21,7 +21,15 @@ def rot(q, ctrl=()):
     return eng.op_record(eng.OP_U2, q, [c, -1j * sn, -1j * sn, c], controls=ctrl)
 
 
+import os
+ONLY = os.environ.get("SWEEP_ONLY", "")
+
+
 def timeit(ops, reps=5, label=""):
+    if ONLY and not any(tok in label for tok in ONLY.split("|")):
+        return 0.0
+    if ONLY:
+        reps = 1
     plan = eng.Plan(n, np.concatenate(ops), eng.PLAN_FUSE)
     info = plan.info()
     for _ in range(2):
