@@ -40,3 +40,35 @@ def qft(n: int):
         for j in range(i):
             gates.append(("CPhase", j, i, float(pi / np.float32(1 << (i - j)))))
     return gates
+
+
+def to_ops(gates):
+    """Lower workload gate tuples straight to engine ops (struct aqs_op records), for states beyond the
+    30-qubit limit of the drop-in QCircuit API.  Matrices as in the host layer."""
+    from . import engine as eng
+    h = np.float32(0.70710678118)
+    recs = []
+    for g in gates:
+        name = g[0]
+        if name == "H":
+            recs.append(eng.op_record(eng.OP_U2, g[1], [h, h, h, -h]))
+        elif name == "X":
+            recs.append(eng.op_record(eng.OP_X, g[1]))
+        elif name == "CX":
+            recs.append(eng.op_record(eng.OP_X, g[2], controls=(g[1],)))
+        elif name in ("RotX", "RotY", "RotZ"):
+            a = np.float32(g[2])
+            c, s = np.cos(a / np.float32(2), dtype=np.float32), np.sin(a / np.float32(2), dtype=np.float32)
+            if name == "RotX":
+                recs.append(eng.op_record(eng.OP_U2, g[1], [c, complex(0, -s), complex(0, -s), c]))
+            elif name == "RotY":
+                recs.append(eng.op_record(eng.OP_U2, g[1], [c, -s, s, c]))
+            else:
+                recs.append(eng.op_record(eng.OP_DIAG, g[1], [complex(c, -s), 0, 0, complex(c, s)]))
+        elif name == "CPhase":
+            a = np.float32(g[3])
+            recs.append(eng.op_record(eng.OP_DIAG, g[2], [1, 0, 0, complex(np.cos(a, dtype=np.float32), np.sin(a, dtype=np.float32))],
+                                      controls=(g[1],)))
+        else:
+            raise KeyError(name)
+    return np.concatenate(recs) if recs else eng.make_ops(0)
