@@ -168,11 +168,15 @@ static int build_fused(aqs_plan_s* p) {
     const uint64_t lane_mask = (1ull << kLaneBits) - 1ull;
 
     std::vector<CanonOp> ops = simplify(n, p->ops);
-    std::vector<int> cand(ops.size());
-    for (size_t i = 0; i < ops.size(); ++i) cand[i] = (int)i;
-
-    std::vector<int> taken, rest;
-    while (!cand.empty()) {
+    // Sliding window over the op stream: a pass looks at the ops deferred by earlier passes plus
+    // the next kWindow ops, so planning is O(passes * window) even for million-op circuits
+    // (Grover-26 with 6433 iterations lowers to ~1e6 ops).
+    const size_t kWindow = 4096;
+    size_t next = 0;
+    std::vector<int> cand, taken, rest;
+    while (true) {
+        while (cand.size() < kWindow && next < ops.size()) cand.push_back((int)next++);
+        if (cand.empty()) break;
         uint64_t tile = greedy_group(ops, cand, lane_mask, all_bits, T - kLaneBits, taken, rest);
         if (taken.empty()) return fail(AQS_ERR_STATE, "fusion planner made no progress");
         // pad the tile to exactly T bits with the lowest unused positions

@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--draws", type=int, default=1000)
+    ap.add_argument("--workload", default="brickwork", choices=["brickwork", "qft"],
+                    help="brickwork = the headline circuit; qft = fourier_transform(n) (BASELINE configs 2 and 5)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -264,12 +266,15 @@ def run_ours(args):
         d2h = c1["d2h_bytes"] - c0["d2h_bytes"]
         return out
 
-    for _ in range(min(W, 2) or 1):
+    for _ in range(max(1, W)):
         e2e_step()
     barrier()
+    e2e_steps = []
     t0 = time.perf_counter()
     for _ in range(K):
-        e2e_step()
+        t1 = time.perf_counter()
+        e2e_step()                      # returns after the D2H read of the outcomes
+        e2e_steps.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
     barrier()
@@ -292,7 +297,7 @@ def run_ours(args):
             "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one circuit per GPU)",
             "l2": "state is 8 GiB >> 126 MB L2: every pass streams from HBM, no flush needed",
         },
-        "e2e": {"value": e2e_value, "unit": "gate-apps/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": e2e_value, "unit": "gate-apps/s", "ms_per_step": e2e_ms, "steps_ms": [round(x, 1) for x in e2e_steps],
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "what": "QCircuit build + QSimulator(n) + simulate (plan build, descriptor upload) + 1000-draw sample readback, host wall clock"},
         "gpu_launches": int(launches_f),
@@ -326,7 +331,8 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
     from afquantumsim_b200.sharded import ShardedState
     g = int(np.log2(world))
     n, K, W = args.qubits + g, args.steps, max(args.warmup, 0)
-    gates = wl.brickwork(n, args.depth)
+    make_gates = (lambda: wl.qft(n)) if args.workload == "qft" else (lambda: wl.brickwork(n, args.depth))
+    gates = make_gates()
     ops = wl.to_ops(gates)
     S_shard = 8.0 * (1 << (n - g))
     st = ShardedState(n)
@@ -366,7 +372,7 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
 
     def e2e_step():
         s2 = ShardedState(n)
-        s2.apply_ops(wl.to_ops(wl.brickwork(n, args.depth)))
+        s2.apply_ops(wl.to_ops(make_gates()))
         return s2.sample(u)
 
     del st
@@ -394,8 +400,8 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
         "config": {
-            "workload": f"brickwork-{n} depth {args.depth}: {gate_apps} gate applications on ONE 2^{n} state, "
-                        f"numpy PCG64 seed {n}; {S_shard / 2**30:.0f} GiB shard per GPU",
+            "workload": (f"brickwork-{n} depth {args.depth}" if args.workload == "brickwork" else f"fourier_transform({n})")
+                        + f": {gate_apps} gate applications on ONE 2^{n} state; {S_shard / 2**30:.0f} GiB shard per GPU",
             "parallelism": f"state sharded over {world} GPUs on the top {g} qubits; half-shard NCCL send/recv per global-qubit swap",
             "fusion": "on", "l2": "shard is 8 GiB >> 126 MB L2",
         },
