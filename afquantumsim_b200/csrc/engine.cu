@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -178,11 +179,92 @@ int launch_canon(float2* a, int n, const CanonOp& c, cudaStream_t st) {
     return launch_items(k_pair<1, MK_GENERAL, kPairItems>, A, A.n_items, kThreads * kPairItems, st);
 }
 
+// Device buffers and streams are recycled.  cudaMalloc / cudaFree / cudaStreamDestroy take
+// milliseconds to (measured, on a shared host) hundreds of milliseconds and synchronise the
+// device, and the API's normal use — a QSimulator and a plan per run — would call them every
+// time.  Sizes are rounded to powers of two (>= 256 B) so that buffers are interchangeable.
+struct PoolEntry { void* p; size_t bytes; };
+static std::vector<PoolEntry> g_pool;
+static std::vector<cudaStream_t> g_stream_pool;
+static std::mutex g_pool_mu;
+constexpr size_t kPoolMaxEntries = 16;
+constexpr size_t kPoolMaxBigEntries = 2;            // buffers of 1 GiB and more
+
+static size_t pool_round(size_t bytes) {
+    size_t r = 256;
+    while (r < bytes) r <<= 1;
+    return r;
+}
+cudaError_t pool_alloc(void** out, size_t bytes) {
+    bytes = pool_round(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].bytes == bytes) {
+                *out = g_pool[i].p;
+                g_pool.erase(g_pool.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // give cached buffers back and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto& pe : g_pool) cudaFree(pe.p);
+        g_pool.clear();
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+void pool_free(void* p, size_t bytes) {
+    if (!p) return;
+    bytes = pool_round(bytes);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t big = 0;
+    for (auto& pe : g_pool) big += pe.bytes >= (1ull << 30);
+    if (g_pool.size() >= kPoolMaxEntries || (bytes >= (1ull << 30) && big >= kPoolMaxBigEntries)) {
+        // evict the oldest entry of the same class
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if ((g_pool[i].bytes >= (1ull << 30)) == (bytes >= (1ull << 30)) || g_pool.size() >= kPoolMaxEntries) {
+                cudaFree(g_pool[i].p);
+                g_pool.erase(g_pool.begin() + i);
+                break;
+            }
+    }
+    g_pool.push_back({p, bytes});
+}
+static void pool_release_all() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& pe : g_pool) cudaFree(pe.p);
+    g_pool.clear();
+    for (auto st : g_stream_pool) cudaStreamDestroy(st);
+    g_stream_pool.clear();
+}
+static cudaError_t stream_acquire(cudaStream_t* out) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_stream_pool.empty()) {
+            *out = g_stream_pool.back();
+            g_stream_pool.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+static void stream_release(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_stream_pool.size() < 16) g_stream_pool.push_back(st);
+    else cudaStreamDestroy(st);
+}
+
 static int ensure_scratch(aqs_state_s* s, size_t bytes) {
     if (s->scratch_bytes >= bytes) return AQS_OK;
-    if (s->scratch) cudaFree(s->scratch);
+    if (s->scratch) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        pool_free(s->scratch, s->scratch_bytes);
+    }
     s->scratch = nullptr; s->scratch_bytes = 0;
-    CUDA_TRY(cudaMalloc(&s->scratch, bytes));
+    CUDA_TRY(pool_alloc(&s->scratch, bytes));
     s->scratch_bytes = bytes;
     return AQS_OK;
 }
@@ -225,6 +307,7 @@ int aqs_engine_init(int device) {
 }
 
 int aqs_engine_shutdown(void) {
+    pool_release_all();
     g_inited = false;
     return AQS_OK;
 }
@@ -247,10 +330,11 @@ int aqs_state_create(int n, aqs_state_t* out) {
     s->n = n;
     s->N = 1ull << n;
     const size_t bytes = std::max<size_t>(s->N * sizeof(float2), 16);
-    cudaError_t e = cudaMalloc((void**)&s->d, bytes);
+    cudaError_t e = pool_alloc((void**)&s->d, bytes);
     if (e != cudaSuccess) { delete s; return fail_cuda(e, "cudaMalloc(state)", __LINE__); }
-    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { cudaFree(s->d); delete s; return fail_cuda(e, "cudaStreamCreate", __LINE__); }
+    s->alloc_bytes = bytes;
+    e = stream_acquire(&s->stream);
+    if (e != cudaSuccess) { pool_free(s->d, bytes); delete s; return fail_cuda(e, "cudaStreamCreate", __LINE__); }
     s->own_stream = true;
     *out = s;
     return aqs_state_set_basis(s, 0);
@@ -268,7 +352,7 @@ int aqs_state_wrap(int n, void* device_ptr, aqs_state_t* out) {
     s->N = 1ull << n;
     s->d = (float2*)device_ptr;
     s->own_memory = false;
-    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    cudaError_t e = stream_acquire(&s->stream);
     if (e != cudaSuccess) { delete s; return fail_cuda(e, "cudaStreamCreate", __LINE__); }
     s->own_stream = true;
     *out = s;
@@ -278,9 +362,9 @@ int aqs_state_wrap(int n, void* device_ptr, aqs_state_t* out) {
 int aqs_state_destroy(aqs_state_t s) {
     if (!s) return AQS_OK;
     cudaStreamSynchronize(s->stream);
-    if (s->scratch) cudaFree(s->scratch);
-    if (s->d && s->own_memory) cudaFree(s->d);
-    if (s->own_stream) cudaStreamDestroy(s->stream);
+    if (s->scratch) pool_free(s->scratch, s->scratch_bytes);
+    if (s->d && s->own_memory) pool_free(s->d, s->alloc_bytes);
+    if (s->own_stream) stream_release(s->stream);
     delete s;
     return AQS_OK;
 }
@@ -369,7 +453,7 @@ int aqs_state_device_ptr(aqs_state_t s, void** dptr) {
 int aqs_state_set_stream(aqs_state_t s, void* stream) {
     REQUIRE(s, "null handle");
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (s->own_stream) cudaStreamDestroy(s->stream);
+    if (s->own_stream) stream_release(s->stream);
     s->stream = (cudaStream_t)stream;
     s->own_stream = false;
     return AQS_OK;
@@ -470,12 +554,13 @@ int aqs_probabilities(aqs_state_t s, float* host_out, uint64_t offset, uint64_t 
     REQUIRE(offset <= s->N && count <= s->N - offset, "range outside the state");
     if (count == 0) return AQS_OK;
     float* tmp = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&tmp, count * sizeof(float)));
+    CUDA_TRY(pool_alloc((void**)&tmp, count * sizeof(float)));
     k_probabilities<<<stream_blocks(count), 256, 0, s->stream>>>(s->d + offset, count, tmp);
     count_launch(1);
     cudaError_t e = cudaMemcpyAsync(host_out, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(tmp);
+    else cudaStreamSynchronize(s->stream);
+    pool_free(tmp, count * sizeof(float));
     if (e != cudaSuccess) return fail_cuda(e, "probabilities copy", __LINE__);
     c_d2h += count * sizeof(float);
     return AQS_OK;
@@ -511,9 +596,9 @@ static int sample_impl(aqs_state_t s, const float* u_host, const uint64_t* ufix_
     unsigned long long* out_dev = (unsigned long long*)(base + off_o);
     uint32_t* hist_dev = nullptr;
     if (hist_host) {
-        CUDA_TRY(cudaMalloc((void**)&hist_dev, s->N * sizeof(uint32_t)));
+        CUDA_TRY(pool_alloc((void**)&hist_dev, s->N * sizeof(uint32_t)));
         cudaError_t e = cudaMemsetAsync(hist_dev, 0, s->N * sizeof(uint32_t), s->stream);
-        if (e != cudaSuccess) { cudaFree(hist_dev); return fail_cuda(e, "hist memset", __LINE__); }
+        if (e != cudaSuccess) { pool_free(hist_dev, s->N * sizeof(uint32_t)); return fail_cuda(e, "hist memset", __LINE__); }
     }
     k_tile_sums<<<(unsigned)n_tiles, 256, 0, s->stream>>>(s->d, tile_amps, sums);
     k_scan_tiles<<<1, 1024, 0, s->stream>>>(sums, n_tiles);
@@ -541,7 +626,8 @@ static int sample_impl(aqs_state_t s, const float* u_host, const uint64_t* ufix_
         c_d2h += s->N * sizeof(uint32_t);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    if (hist_dev) cudaFree(hist_dev);
+    else cudaStreamSynchronize(s->stream);
+    if (hist_dev) pool_free(hist_dev, s->N * sizeof(uint32_t));
     if (e != cudaSuccess) return fail_cuda(e, "sampling", __LINE__);
     return AQS_OK;
 }

@@ -14,6 +14,7 @@ struct aqs_state_s {
     float2* d = nullptr;          // 2^n complex64, interleaved, in HBM
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    size_t alloc_bytes = 0;       // size of the pooled allocation behind d
     bool own_memory = true;       // false for aqs_state_wrap (caller-owned allocation)
     void* scratch = nullptr;      // reductions / sampling workspace
     size_t scratch_bytes = 0;
@@ -43,6 +44,9 @@ int sm_count();
 int canonicalize(int n, const aqs_op& op, CanonOp& out);
 double op_bytes(int n, const CanonOp& c);
 int launch_canon(float2* a, int n, const CanonOp& c, cudaStream_t st);   // one per-gate kernel
+
+cudaError_t pool_alloc(void** out, size_t bytes);   // recycled device buffers (engine.cu)
+void pool_free(void* p, size_t bytes);
 
 int fused_init();   // opt-in shared-memory size etc. for the tile kernel
 

@@ -43,6 +43,10 @@ struct aqs_plan_s {
     std::vector<aqs::FusedPass> passes;  // fused path (empty => run ops one by one)
     void* arena = nullptr;               // device copy of all segment/op descriptors
     size_t arena_bytes = 0;
+    cudaGraphExec_t graph = nullptr;     // AQS_PLAN_GRAPH: the launch sequence captured for `graph_state`
+    const void* graph_state = nullptr;
+    cudaStream_t last_stream = nullptr;  // stream of the most recent run (synchronised before the arena is recycled)
+    bool ran = false;
     aqs_plan_info info{};
 };
 
@@ -81,19 +85,27 @@ static void reclassify(CanonOp& c) {
     }
 }
 
-// step 1: SWAP -> 3 flips; merge uncontrolled 1-qubit runs; drop identities
+// step 1: SWAP -> 3 flips; merge uncontrolled 1-qubit gates on the same qubit; drop identities.
+// A pending DIAGONAL 1-qubit gate stays mergeable across ops that use its qubit only as a
+// control or diagonal target (it commutes with them): e.g. RotZ on the control qubit of a CX
+// slides through the CX and fuses with the next rotation on that qubit.  The merged gate is
+// emitted at the LATER position (the pending diagonal moves forward, never the later gate back).
 static std::vector<CanonOp> simplify(int n, const std::vector<CanonOp>& in) {
     std::vector<CanonOp> out;
     std::vector<int> open(n, -1);   // index in `out` of a mergeable uncontrolled 1q op per bit
-    auto touch = [&](uint64_t bits) {
-        for (int b = 0; b < n; ++b)
-            if (bits >> b & 1ull) open[b] = -1;
+    auto close_bits = [&](uint64_t nd, uint64_t dg) {
+        for (int b = 0; b < n; ++b) {
+            if (open[b] < 0) continue;
+            if (nd >> b & 1ull) open[b] = -1;
+            else if ((dg >> b & 1ull) && out[open[b]].kind != AQS_OP_DIAG) open[b] = -1;
+        }
     };
     auto push = [&](const CanonOp& c) {
         if (c.identity) return;
         if (c.cmask == 0 && c.kind != AQS_OP_SWAP) {
             if (open[c.p] >= 0) {
                 CanonOp& prev = out[open[c.p]];
+                const bool adjacent = (open[c.p] == (int)out.size() - 1);
                 float2 A[4], B[4], C[4];
                 full_matrix(prev, A);
                 full_matrix(c, B);
@@ -101,15 +113,24 @@ static std::vector<CanonOp> simplify(int n, const std::vector<CanonOp>& in) {
                 C[1] = caddh(cmulh(B[0], A[1]), cmulh(B[1], A[3]));
                 C[2] = caddh(cmulh(B[2], A[0]), cmulh(B[3], A[2]));
                 C[3] = caddh(cmulh(B[2], A[1]), cmulh(B[3], A[3]));
-                for (int i = 0; i < 4; ++i) prev.m[i] = C[i];
-                reclassify(prev);
+                if (adjacent) {
+                    for (int i = 0; i < 4; ++i) prev.m[i] = C[i];
+                    reclassify(prev);
+                } else {
+                    CanonOp merged = prev;
+                    for (int i = 0; i < 4; ++i) merged.m[i] = C[i];
+                    reclassify(merged);
+                    prev.identity = true;                 // the pending gate moves forward to here
+                    out.push_back(merged);
+                    open[c.p] = (int)out.size() - 1;
+                }
                 return;
             }
             out.push_back(c);
             open[c.p] = (int)out.size() - 1;
             return;
         }
-        touch(c.cmask | (1ull << c.p));
+        close_bits(nd_bits(c) | (c.kind == AQS_OP_SWAP ? ((1ull << c.p) | (1ull << c.p2)) : 0ull), d_bits(c));
         out.push_back(c);
     };
     for (const CanonOp& c : in) {
@@ -161,6 +182,34 @@ static uint64_t greedy_group(const std::vector<CanonOp>& ops, const std::vector<
     return bits;
 }
 
+// Grow a bit set one bit at a time, each time adding the candidate bit that lets a group take
+// the most ops from the head of `cand` (ops whose target lies on a chosen non-lane bit weigh
+// more: lane-only and diagonal ops fit any group).
+static uint64_t choose_bits(const std::vector<CanonOp>& ops, const std::vector<int>& cand, uint64_t base, uint64_t pool_limit,
+                            int count, int n) {
+    const uint64_t lane_mask = (1ull << kLaneBits) - 1ull;
+    const size_t kScore = std::min<size_t>(cand.size(), 768);
+    std::vector<int> head(cand.begin(), cand.begin() + kScore), t2, r2;
+    uint64_t chosen = base, pool = 0;
+    for (int idx : head) pool |= nd_bits(ops[idx]);
+    pool &= pool_limit & ~base;
+    for (int step = 0; step < count && pool; ++step) {
+        int best_bit = -1;
+        size_t best = 0;
+        for (int b = 0; b < n; ++b) {
+            if (!(pool >> b & 1ull)) continue;
+            greedy_group(ops, head, chosen | (1ull << b), chosen | (1ull << b), 0, t2, r2);
+            size_t gain = 0;
+            for (int idx : t2) gain += (nd_bits(ops[idx]) & ~lane_mask) ? 4 : 1;
+            if (best_bit < 0 || gain > best) { best = gain; best_bit = b; }
+        }
+        if (best_bit < 0) break;
+        chosen |= 1ull << best_bit;
+        pool &= ~(1ull << best_bit);
+    }
+    return chosen;
+}
+
 static int build_fused(aqs_plan_s* p) {
     const int n = p->n;
     const int T = std::min(n, kMaxTileBits);
@@ -177,7 +226,17 @@ static int build_fused(aqs_plan_s* p) {
     while (true) {
         while (cand.size() < kWindow && next < ops.size()) cand.push_back((int)next++);
         if (cand.empty()) break;
-        uint64_t tile = greedy_group(ops, cand, lane_mask, all_bits, T - kLaneBits, taken, rest);
+        // Tile choice.  Plain first-come filling scatters the tile over whatever targets come
+        // first; for nearest-neighbour circuits a better set exists.  Grow the tile one bit at a
+        // time, each time adding the bit that lets the pass take the most ops from the head of
+        // the window (skipped for huge op lists, where planning time matters more).
+        uint64_t tile;
+        if (ops.size() <= 60000) {
+            const uint64_t chosen = choose_bits(ops, cand, lane_mask, all_bits, T - kLaneBits, n);
+            tile = greedy_group(ops, cand, chosen, chosen, 0, taken, rest);
+        } else {
+            tile = greedy_group(ops, cand, lane_mask, all_bits, T - kLaneBits, taken, rest);
+        }
         if (taken.empty()) return fail(AQS_ERR_STATE, "fusion planner made no progress");
         // pad the tile to exactly T bits with the lowest unused positions
         for (int b = 0; b < n && popc(tile) < T; ++b) tile |= 1ull << b;
@@ -316,7 +375,7 @@ static int ensure_uploaded(aqs_plan_s* p) {
     size_t bytes = 0;
     for (auto& fp : p->passes) bytes += pad(fp.segs.size() * sizeof(TileSeg)) + pad(fp.ops.size() * sizeof(TileOp));
     std::vector<char> host(bytes);
-    cudaError_t e = cudaMalloc(&p->arena, bytes);
+    cudaError_t e = pool_alloc(&p->arena, bytes);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(plan arena)", __LINE__);
     p->arena_bytes = bytes;
     size_t off = 0;
@@ -413,12 +472,8 @@ int aqs_plan_build(int n, const aqs_op* ops, uint64_t n_ops, uint32_t flags, aqs
     return AQS_OK;
 }
 
-int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
-    if (!s || !p) return fail(AQS_ERR_INVALID, "null handle");
-    if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
+static int launch_all(aqs_state_t s, aqs_plan_t p) {
     if (!p->passes.empty()) {
-        int up = ensure_uploaded(p);
-        if (up) return up;
         for (const FusedPass& fp : p->passes) {
             int rc = launch_pass(s->d, fp, s->stream);
             if (rc) return rc;
@@ -428,6 +483,41 @@ int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
             int rc = launch_canon(s->d, s->n, c, s->stream);
             if (rc) return rc;
         }
+    }
+    return AQS_OK;
+}
+
+int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
+    if (!s || !p) return fail(AQS_ERR_INVALID, "null handle");
+    if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
+    int up = ensure_uploaded(p);
+    if (up) return up;
+    p->last_stream = s->stream;
+    p->ran = true;
+    if (p->flags & AQS_PLAN_GRAPH) {
+        // launch-bound plans (small states, thousands of passes): replay one CUDA graph instead of
+        // issuing every launch from the host.  The graph bakes in the state's buffer, so it is
+        // re-captured when the plan is run on a different state.
+        if (!p->graph || p->graph_state != (const void*)s->d) {
+            if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaStreamBeginCapture", __LINE__);
+            int rc = launch_all(s, p);
+            e = cudaStreamEndCapture(s->stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture", __LINE__);
+            e = cudaGraphInstantiate(&p->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate", __LINE__);
+            p->graph_state = (const void*)s->d;
+        }
+        cudaError_t e = cudaGraphLaunch(p->graph, s->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaGraphLaunch", __LINE__);
+        count_launch(p->info.n_launches);
+    } else {
+        int rc = launch_all(s, p);
+        if (rc) return rc;
     }
     count_ops(p->ops.size());
     cudaError_t e = cudaGetLastError();
@@ -443,7 +533,9 @@ int aqs_plan_get_info(aqs_plan_t p, aqs_plan_info* info) {
 
 int aqs_plan_destroy(aqs_plan_t p) {
     if (!p) return AQS_OK;
-    if (p->arena) cudaFree(p->arena);
+    if (p->ran && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();   // kernels may still read the arena
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+    if (p->arena) pool_free(p->arena, p->arena_bytes);
     delete p;
     return AQS_OK;
 }

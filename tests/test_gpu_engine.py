@@ -147,6 +147,48 @@ def test_random_circuits_match_oracle(n, gates, seed, fuse):
     assert orc.rel_l2(got, want) < TOL
 
 
+@pytest.mark.parametrize("flags", [eng.PLAN_GRAPH, eng.PLAN_FUSE | eng.PLAN_GRAPH])
+def test_cuda_graph_plans(flags):
+    """AQS_PLAN_GRAPH: captured once, replayed, re-captured for another state."""
+    n = 11
+    circ = random_circuit(n, 120, 31)
+    init = random_state(n, 32)
+    ops = lower_array(circ)
+    plan = eng.Plan(n, ops, flags)
+    want = orc.simulate(init.copy(), circ)
+    for _ in range(2):                      # second state forces a re-capture
+        s = eng.State(n)
+        s.upload(init)
+        s.run(plan)
+        assert orc.rel_l2(s.download(), want) < TOL
+        s.run(plan)                         # replay composes like a second simulate()
+        assert orc.rel_l2(s.download(), orc.simulate(want.copy(), circ)) < TOL
+
+
+def test_state_wrap_and_sample_fixed():
+    import torch
+    n = 12
+    a = random_state(n, 71)
+    buf = torch.from_numpy(a.copy()).cuda()
+    s = eng.State.wrap(n, buf.data_ptr())
+    circ = random_circuit(n, 40, 72)
+    s.apply_ops(lower_array(circ))
+    s.sync()
+    want = orc.simulate(a.copy(), circ)
+    assert orc.rel_l2(buf.cpu().numpy(), want) < TOL          # the kernels ran on the caller's tensor
+    s.upload(want)
+    total = s.prob_fixed()
+    U = np.array([0, total // 3, total - 1, total, total + 5], dtype=np.uint64)
+    got = s.sample_fixed(U)
+    F = (orc.probabilities(want).astype(np.float32) * np.float32(2.0 ** 62)).astype(np.uint64)
+    cs = np.cumsum(F, dtype=np.uint64)
+    exp = np.searchsorted(cs, U, side="right").astype(np.uint64)
+    exp[exp == (1 << n)] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert np.array_equal(got, exp)
+    s.close()
+    assert orc.rel_l2(buf.cpu().numpy(), want) < 1e-7         # wrap does not own (or free) the memory
+
+
 @pytest.mark.parametrize("fuse", [False, True])
 def test_nested_composites_match_oracle(fuse):
     inner = orc.Circ(2, [("H", 0), ("CRotY", 0, 1, 0.7), ("RotZ", 1, -1.3), ("CY", 1, 0), ("Swap", 0, 1)])
