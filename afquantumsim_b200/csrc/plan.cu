@@ -3,33 +3,57 @@
 // Replaces QCircuit::compile (reference src/quantum.cpp:199-210).  The reference
 // multiplies every gate into a dense 2^n x 2^n unitary; here "compiling" turns the
 // op list into a launch plan.  With AQS_PLAN_FUSE the planner
-//   1. splits SWAPs into three controlled flips and merges runs of uncontrolled
-//      single-qubit gates on the same qubit into one 2x2,
-//   2. greedily groups ops into PASSES: a pass owns up to 12 index bits (the low 5
+//   1. rewrites the op list (simplify): SWAP -> three controlled flips; runs of
+//      single-qubit gates on one qubit merge when the product is no more expensive
+//      than its factors; a singly-controlled gate becomes a MULTIPLEXED gate ("matrix
+//      A where the control bit is 0, matrix B where it is 1") and merges with its
+//      neighbours on the target qubit the same way, so a CX followed by a rotation is
+//      one butterfly pass, not two (CX vanishes from brickwork circuits);
+//   2. greedily groups ops into PASSES: a pass owns up to T index bits (the low 5
 //      always, for coalescing) and takes, in program order, every op whose target
 //      lies in those bits, skipping over ops it cannot take as long as the skipped
 //      op commutes with everything taken later (two ops commute when on every
-//      shared bit both act diagonally — as a control or a diagonal target),
-//   3. splits each pass into SEGMENTS by the same rule with 4 register bits,
-//   4. writes device descriptors for fused_kernel.cuh.
-// Diagonal ops and controls never constrain the tile: QFT's CPhase ladder fuses freely.
+//      shared bit both act diagonally — as a control or a diagonal target);
+//   3. splits each pass into SEGMENTS by the same rule with 5 register bits, and
+//      picks for every change of layout an XOR swizzle of shared memory that makes
+//      both sides bank-conflict free;
+//   4. decomposes every 2x2 into in-place shears and writes the descriptors that
+//      tile_kernel.cuh interprets (they travel as kernel parameters).
+// Diagonal ops and controls never constrain a tile: QFT's CPhase ladder fuses freely.
 #include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "engine_internal.h"
-#include "fused_kernel.cuh"
+#include "tile_kernel.cuh"
 
 namespace aqs {
 
+typedef std::complex<double> cd;
+
+// planner op: a (possibly multiplexed, possibly controlled) 2x2 on one target bit
+struct POp {
+    int p = 0;               // target bit
+    uint64_t cmask = 0;      // controls: the op is the identity where (index & cmask) != cval
+    uint64_t cval = 0;
+    int mux = -1;            // bit selecting m[1] over m[0]; -1: m[0] everywhere
+    bool diag = false;       // m[0] diagonal and mux == -1: never constrains a tile
+    bool dead = false;
+    cd m[2][4];              // row-major 2x2
+};
+
 struct FusedPass {
-    TileArgs args;
-    int warps_log2 = 0;
+    int T = 0;
     uint64_t n_tiles = 0;
+    float2 scale = make_float2(1.f, 0.f);
+    bool has_scale = false;
+    BitList tile;
+    uint64_t ld_toff[kMaxThreadBits], ld_roff[kRegBits], st_toff[kMaxThreadBits], st_roff[kRegBits];
     std::vector<TileSeg> segs;
     std::vector<TileOp> ops;
 };
@@ -41,134 +65,321 @@ struct aqs_plan_s {
     uint32_t flags = 0;
     std::vector<aqs::CanonOp> ops;       // per-gate path
     std::vector<aqs::FusedPass> passes;  // fused path (empty => run ops one by one)
-    void* arena = nullptr;               // device copy of all segment/op descriptors
-    size_t arena_bytes = 0;
     cudaGraphExec_t graph = nullptr;     // AQS_PLAN_GRAPH: the launch sequence captured for `graph_state`
     const void* graph_state = nullptr;
-    cudaStream_t last_stream = nullptr;  // stream of the most recent run (synchronised before the arena is recycled)
-    bool ran = false;
     aqs_plan_info info{};
 };
 
 namespace aqs {
 
-int fused_init() { return AQS_OK; }
-
 static inline int popc(uint64_t x) { return __builtin_popcountll(x); }
 
+// ---- 2x2 helpers ------------------------------------------------------------
+static void mat_mul(const cd* B, const cd* A, cd* C) {   // C = B * A
+    cd t[4];
+    t[0] = B[0] * A[0] + B[1] * A[2];
+    t[1] = B[0] * A[1] + B[1] * A[3];
+    t[2] = B[2] * A[0] + B[3] * A[2];
+    t[3] = B[2] * A[1] + B[3] * A[3];
+    for (int i = 0; i < 4; ++i) C[i] = t[i];
+}
+static void mat_identity(cd* M) { M[0] = M[3] = cd(1, 0); M[1] = M[2] = cd(0, 0); }
+static bool z0(cd z) { return std::abs(z) < 1e-14; }
+static bool mat_is_diag(const cd* M) { return z0(M[1]) && z0(M[2]); }
+static bool mat_is_identity(const cd* M) { return mat_is_diag(M) && z0(M[0] - 1.0) && z0(M[3] - 1.0); }
+static bool mat_equal(const cd* A, const cd* B) {
+    for (int i = 0; i < 4; ++i)
+        if (!z0(A[i] - B[i])) return false;
+    return true;
+}
+
+// In-place form of a 2x2 for the tile kernel:  M = Shear3(a, b, g) * diag(sx, sy), with real or
+// imaginary shear coefficients (tile_kernel.cuh, butterfly<>).  Falls back to TK_GEN (the direct
+// 8-instruction form) when the matrix has no such structure or the shears would be ill-conditioned.
+struct Decomp {
+    int kind = TK_GEN;
+    float c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cost = 8;            // FFMA2 per amplitude pair
+};
+
+// N (2x2 real, det 1, N00 >= 0 expected) = [[1+ab, a+g+abg],[b, 1+bg]]
+static bool shear3(double n00, double n01, double n10, double n11, double& a, double& b, double& g) {
+    b = n10;
+    if (std::fabs(b) > 1e-7) {
+        a = (n00 - 1.0) / b;
+        g = (n11 - 1.0) / b;
+    } else {
+        if (std::fabs(n00 - 1.0) > 1e-7 || std::fabs(n11 - 1.0) > 1e-7) return false;
+        a = n01;
+        g = 0.0;
+    }
+    if (std::fabs(a) > 4.0 || std::fabs(g) > 4.0 || std::fabs(b) > 4.0) return false;
+    const double r00 = 1 + a * b, r01 = a + g + a * b * g, r10 = b, r11 = 1 + b * g;
+    const double err = std::max(std::max(std::fabs(r00 - n00), std::fabs(r01 - n01)), std::max(std::fabs(r10 - n10), std::fabs(r11 - n11)));
+    return err < 1e-9;
+}
+
+static Decomp decompose(const cd* M) {
+    Decomp d;
+    auto gen = [&]() {
+        d.kind = TK_GEN;
+        d.cost = 8;
+        for (int i = 0; i < 4; ++i) { d.c[2 * i] = (float)M[i].real(); d.c[2 * i + 1] = (float)M[i].imag(); }
+        return d;
+    };
+    const bool re00 = std::fabs(M[0].imag()) < 1e-14, re01 = std::fabs(M[1].imag()) < 1e-14;
+    const bool re10 = std::fabs(M[2].imag()) < 1e-14, re11 = std::fabs(M[3].imag()) < 1e-14;
+    const bool im00 = std::fabs(M[0].real()) < 1e-14, im01 = std::fabs(M[1].real()) < 1e-14;
+    const bool im10 = std::fabs(M[2].real()) < 1e-14, im11 = std::fabs(M[3].real()) < 1e-14;
+    if (z0(M[0]) && z0(M[3])) {
+        // anti-diagonal: pure data movement, kept exact (X, CX, Swap, Y)
+        if (re01 && re10) { d.kind = TK_PERM_R; d.c[0] = (float)M[1].real(); d.c[1] = (float)M[2].real(); d.cost = 2; return d; }
+        if (im01 && im10) { d.kind = TK_PERM_I; d.c[0] = (float)M[1].imag(); d.c[1] = (float)M[2].imag(); d.cost = 2; return d; }
+        return gen();
+    }
+    double A, B, C, D;   // the four real numbers of the structured matrix
+    int cls;             // 0 real, 1 XLIKE [[A, iB],[iC, D]], 2 AXLIKE [[iA, B],[C, iD]]
+    if (re00 && re01 && re10 && re11) { cls = 0; A = M[0].real(); B = M[1].real(); C = M[2].real(); D = M[3].real(); }
+    else if (re00 && re11 && im01 && im10) { cls = 1; A = M[0].real(); B = M[1].imag(); C = M[2].imag(); D = M[3].real(); }
+    else if (im00 && im11 && re01 && re10) { cls = 2; A = M[0].imag(); B = -M[1].real(); C = -M[2].real(); D = M[3].imag(); }
+    else return gen();
+    const double det = (cls == 0) ? (A * D - B * C) : (A * D + B * C);
+    if (std::fabs(det) < 1e-12) return gen();
+    double sx, sy, a, b, g;
+    // Unitary case first (every reference gate): the float entries are orthonormal only to ~1e-7,
+    // so take the exact rotation nearest to M — parametrised by its angle — rather than solving the
+    // shear equations for a matrix whose determinant is not quite 1 (that error would be divided by b).
+    const double orth = (cls == 0) ? (A * B + C * D) : (A * B - C * D);
+    if (std::fabs(A * A + C * C - 1.0) < 2e-6 && std::fabs(B * B + D * D - 1.0) < 2e-6 && std::fabs(orth) < 2e-6) {
+        sx = (A >= 0 ? 1.0 : -1.0);
+        sy = (det >= 0 ? sx : -sx);
+        const double phi = std::atan2(C / sx, A / sx);      // |phi| <= pi/2
+        b = std::sin(phi);
+        a = g = (cls == 0 ? -1.0 : 1.0) * std::tan(0.5 * phi);
+    } else {
+        const double r = std::sqrt(std::fabs(det));
+        sx = (A >= 0 ? r : -r);
+        sy = det / sx;
+        const double n00 = A / sx, n10 = C / sx, n01 = B / sy, n11 = D / sy;
+        if (cls == 0) {
+            if (!shear3(n00, n01, n10, n11, a, b, g)) return gen();
+        } else {
+            // imaginary shears: [[n00, i n01],[i n10, n11]] = [[1-ab, i(a+g-abg)],[ib, 1-bg]]
+            b = n10;
+            if (std::fabs(b) > 1e-7) { a = (1.0 - n00) / b; g = (1.0 - n11) / b; }
+            else if (std::fabs(n00 - 1.0) < 1e-7 && std::fabs(n11 - 1.0) < 1e-7) { a = n01; g = 0.0; }
+            else return gen();
+            const double q00 = 1 - a * b, q01 = a + g - a * b * g, q11 = 1 - b * g;
+            const double err = std::max(std::max(std::fabs(q00 - n00), std::fabs(q01 - n01)), std::fabs(q11 - n11));
+            if (err > 1e-9 || std::fabs(a) > 4.0 || std::fabs(g) > 4.0 || std::fabs(b) > 4.0) return gen();
+        }
+    }
+    const bool unit = sx == 1.0 && sy == 1.0;
+    d.c[0] = (float)a; d.c[1] = (float)b; d.c[2] = (float)g; d.c[3] = (float)sx; d.c[4] = (float)sy;
+    if (cls == 0) { d.kind = unit ? TK_SHR : TK_SHR_P; }
+    else if (cls == 1) { d.kind = unit ? TK_SHI : TK_SHI_P; }
+    else { d.kind = TK_SHI_Q; }
+    d.cost = (d.kind == TK_SHR || d.kind == TK_SHI) ? 3 : 5;
+    return d;
+}
+
+// cost model (FFMA2 per amplitude pair) used to decide merges
+static int mat_cost(const cd* M) {
+    if (mat_is_identity(M)) return 0;
+    if (mat_is_diag(M)) return z0(M[0] - 1.0) ? 1 : 2;
+    return decompose(M).cost;
+}
+static int pop_cost2(const POp& o) {   // twice the average cost over the two branches
+    return o.mux < 0 ? 2 * mat_cost(o.m[0]) : mat_cost(o.m[0]) + mat_cost(o.m[1]);
+}
+
 // bits on which the op acts NON-diagonally / diagonally
-static inline uint64_t nd_bits(const CanonOp& c) { return (c.kind == AQS_OP_U2 || c.kind == AQS_OP_X) ? (1ull << c.p) : 0ull; }
-static inline uint64_t d_bits(const CanonOp& c) { return c.cmask | (c.kind == AQS_OP_DIAG ? (1ull << c.p) : 0ull); }
+static inline uint64_t nd_bits(const POp& c) { return c.diag ? 0ull : (1ull << c.p); }
+static inline uint64_t d_bits(const POp& c) {
+    return c.cmask | (c.mux >= 0 ? (1ull << c.mux) : 0ull) | (c.diag ? (1ull << c.p) : 0ull);
+}
 
-static inline float2 cmulh(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-static inline float2 caddh(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-static bool is0(float2 z) { return z.x == 0.f && z.y == 0.f; }
-static bool is1(float2 z) { return z.x == 1.f && z.y == 0.f; }
-
-static void full_matrix(const CanonOp& c, float2 m[4]) {
+// ---- step 1: rewrite --------------------------------------------------------
+static POp from_canon(const CanonOp& c) {
+    POp o;
+    o.p = c.p;
+    o.cmask = c.cmask;
+    o.cval = c.cval;
     if (c.kind == AQS_OP_X) {
-        m[0] = m[3] = make_float2(0.f, 0.f);
-        m[1] = m[2] = make_float2(1.f, 0.f);
+        o.m[0][0] = o.m[0][3] = cd(0, 0);
+        o.m[0][1] = o.m[0][2] = cd(1, 0);
     } else {
-        for (int i = 0; i < 4; ++i) m[i] = c.m[i];
+        for (int i = 0; i < 4; ++i) o.m[0][i] = cd(c.m[i].x, c.m[i].y);
     }
-}
-static void reclassify(CanonOp& c) {
-    if (is0(c.m[1]) && is0(c.m[2])) {
-        c.kind = AQS_OP_DIAG;
-        c.d0_one = is1(c.m[0]);
-        c.identity = c.d0_one && is1(c.m[3]);
-    } else if (is0(c.m[0]) && is0(c.m[3]) && is1(c.m[1]) && is1(c.m[2])) {
-        c.kind = AQS_OP_X; c.d0_one = false; c.identity = false;
-    } else {
-        c.kind = AQS_OP_U2; c.d0_one = false; c.identity = false;
-    }
+    o.diag = (c.kind == AQS_OP_DIAG);
+    mat_identity(o.m[1]);
+    return o;
 }
 
-// step 1: SWAP -> 3 flips; merge uncontrolled 1-qubit gates on the same qubit; drop identities.
-// A pending DIAGONAL 1-qubit gate stays mergeable across ops that use its qubit only as a
-// control or diagonal target (it commutes with them): e.g. RotZ on the control qubit of a CX
-// slides through the CX and fuses with the next rotation on that qubit.  The merged gate is
-// emitted at the LATER position (the pending diagonal moves forward, never the later gate back).
-static std::vector<CanonOp> simplify(int n, const std::vector<CanonOp>& in) {
-    std::vector<CanonOp> out;
-    std::vector<int> open(n, -1);   // index in `out` of a mergeable uncontrolled 1q op per bit
-    auto close_bits = [&](uint64_t nd, uint64_t dg) {
+static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
+    std::vector<POp> out;
+    out.reserve(in.size() + 16);
+    std::vector<int> open(n, -1);      // index in `out` of an uncontrolled op on bit b that later ops may merge into
+    std::vector<int> last_nd(n, -1);   // index in `out` of the last op acting non-diagonally on bit b
+
+    auto touch = [&](uint64_t nd, uint64_t dg) {
         for (int b = 0; b < n; ++b) {
             if (open[b] < 0) continue;
             if (nd >> b & 1ull) open[b] = -1;
-            else if ((dg >> b & 1ull) && out[open[b]].kind != AQS_OP_DIAG) open[b] = -1;
+            else if ((dg >> b & 1ull) && !out[open[b]].diag) open[b] = -1;
         }
     };
-    auto push = [&](const CanonOp& c) {
-        if (c.identity) return;
-        if (c.cmask == 0 && c.kind != AQS_OP_SWAP) {
-            if (open[c.p] >= 0) {
-                CanonOp& prev = out[open[c.p]];
-                const bool adjacent = (open[c.p] == (int)out.size() - 1);
-                float2 A[4], B[4], C[4];
-                full_matrix(prev, A);
-                full_matrix(c, B);
-                C[0] = caddh(cmulh(B[0], A[0]), cmulh(B[1], A[2]));
-                C[1] = caddh(cmulh(B[0], A[1]), cmulh(B[1], A[3]));
-                C[2] = caddh(cmulh(B[2], A[0]), cmulh(B[3], A[2]));
-                C[3] = caddh(cmulh(B[2], A[1]), cmulh(B[3], A[3]));
-                if (adjacent) {
-                    for (int i = 0; i < 4; ++i) prev.m[i] = C[i];
-                    reclassify(prev);
-                } else {
-                    CanonOp merged = prev;
-                    for (int i = 0; i < 4; ++i) merged.m[i] = C[i];
-                    reclassify(merged);
-                    prev.identity = true;                 // the pending gate moves forward to here
-                    out.push_back(merged);
-                    open[c.p] = (int)out.size() - 1;
-                }
+    auto append = [&](const POp& o) {
+        touch(nd_bits(o), d_bits(o));
+        out.push_back(o);
+        const int idx = (int)out.size() - 1;
+        if (o.cmask == 0) open[o.p] = idx;
+        if (!o.diag) last_nd[o.p] = idx;
+    };
+    // U (uncontrolled, unmultiplexed, on bit t) arrives
+    auto push_plain = [&](const POp& u) {
+        const int t = u.p;
+        if (open[t] >= 0) {
+            POp& w = out[open[t]];
+            if (w.diag && u.diag) {                       // diagonal * diagonal, in place
+                mat_mul(u.m[0], w.m[0], w.m[0]);
                 return;
             }
-            out.push_back(c);
-            open[c.p] = (int)out.size() - 1;
+            if (!w.diag) {
+                // everything between w and here leaves bit t alone, so u commutes back to w
+                POp prod = w;
+                mat_mul(u.m[0], w.m[0], prod.m[0]);
+                if (w.mux >= 0) mat_mul(u.m[0], w.m[1], prod.m[1]);
+                if (pop_cost2(prod) <= pop_cost2(w) + pop_cost2(u)) {
+                    w = prod;
+                    return;
+                }
+            } else {
+                // pending diagonal w, non-diagonal u: w may slide forward to u (ops in between touch t only diagonally)
+                POp prod = u;
+                mat_mul(u.m[0], w.m[0], prod.m[0]);
+                if (pop_cost2(prod) <= pop_cost2(w) + pop_cost2(u)) {
+                    w.dead = true;
+                    open[t] = -1;
+                    append(prod);
+                    return;
+                }
+            }
+        }
+        append(u);
+    };
+    // a gate with exactly one control c (value v) on target t: multiplexed form
+    auto push_ctrl1 = [&](const POp& u, int c, int v) {
+        const int t = u.p;
+        if (open[t] >= 0) {
+            POp& w = out[open[t]];
+            if (!w.diag && (w.mux < 0 || w.mux == c) && last_nd[c] < open[t]) {
+                POp prod = w;
+                if (w.mux < 0) {
+                    for (int i = 0; i < 4; ++i) prod.m[1][i] = w.m[0][i];
+                    prod.mux = c;
+                }
+                mat_mul(u.m[0], prod.m[v], prod.m[v]);
+                // u alone would cost mat_cost(u) on one branch and nothing on the other
+                if (pop_cost2(prod) <= pop_cost2(w) + mat_cost(u.m[0])) {
+                    // w now reads bit c: a non-diagonal op pending on c can no longer accept later merges
+                    if (open[c] >= 0 && !out[open[c]].diag) open[c] = -1;
+                    w = prod;
+                    return;
+                }
+            }
+        }
+        POp o = u;
+        o.cmask = 0; o.cval = 0;
+        o.mux = c;
+        if (v == 1) {
+            for (int i = 0; i < 4; ++i) o.m[1][i] = u.m[0][i];
+            mat_identity(o.m[0]);
+        } else {
+            mat_identity(o.m[1]);
+        }
+        append(o);
+    };
+    auto push = [&](const POp& o) {
+        if (o.diag) {
+            if (o.cmask == 0) {
+                if (mat_is_identity(o.m[0])) return;
+                push_plain(o);
+            } else {
+                append(o);
+            }
             return;
         }
-        close_bits(nd_bits(c) | (c.kind == AQS_OP_SWAP ? ((1ull << c.p) | (1ull << c.p2)) : 0ull), d_bits(c));
-        out.push_back(c);
+        if (o.cmask == 0) {
+            if (mat_is_identity(o.m[0])) return;
+            push_plain(o);
+        } else if (popc(o.cmask) == 1) {
+            const int c = __builtin_ctzll(o.cmask);
+            push_ctrl1(o, c, (int)((o.cval >> c) & 1ull));
+        } else {
+            append(o);
+        }
     };
+
     for (const CanonOp& c : in) {
+        if (c.identity) continue;
         if (c.kind == AQS_OP_SWAP) {
             // swap(a,b) = flip(b | a) flip(a | b) flip(b | a), each under the swap's own controls
             CanonOp f = c;
             f.kind = AQS_OP_X; f.p2 = -1;
             const int a = c.p, b = c.p2;
-            f.p = b; f.cmask = c.cmask | (1ull << a); f.cval = c.cval | (1ull << a); push(f);
-            f.p = a; f.cmask = c.cmask | (1ull << b); f.cval = c.cval | (1ull << b); push(f);
-            f.p = b; f.cmask = c.cmask | (1ull << a); f.cval = c.cval | (1ull << a); push(f);
+            f.p = b; f.cmask = c.cmask | (1ull << a); f.cval = c.cval | (1ull << a); push(from_canon(f));
+            f.p = a; f.cmask = c.cmask | (1ull << b); f.cval = c.cval | (1ull << b); push(from_canon(f));
+            f.p = b; f.cmask = c.cmask | (1ull << a); f.cval = c.cval | (1ull << a); push(from_canon(f));
         } else {
-            push(c);
+            push(from_canon(c));
         }
     }
-    // merged ops may have become identities
-    std::vector<CanonOp> kept;
+
+    // normalise: drop identities, unmultiplex equal branches, turn diagonal results into diagonal ops
+    std::vector<POp> kept;
     kept.reserve(out.size());
-    for (const CanonOp& c : out)
-        if (!c.identity) kept.push_back(c);
+    for (POp& o : out) {
+        if (o.dead) continue;
+        if (o.mux >= 0 && mat_equal(o.m[0], o.m[1])) o.mux = -1;
+        if (o.mux < 0) {
+            if (mat_is_identity(o.m[0])) continue;
+            if (!o.diag && mat_is_diag(o.m[0])) o.diag = true;
+            kept.push_back(o);
+        } else if (mat_is_diag(o.m[0]) && mat_is_diag(o.m[1])) {
+            for (int v = 0; v < 2; ++v) {
+                if (mat_is_identity(o.m[v])) continue;
+                POp dgn;
+                dgn.p = o.p;
+                dgn.cmask = o.cmask | (1ull << o.mux);
+                dgn.cval = o.cval | ((uint64_t)v << o.mux);
+                dgn.diag = true;
+                for (int i = 0; i < 4; ++i) dgn.m[0][i] = o.m[v][i];
+                mat_identity(dgn.m[1]);
+                kept.push_back(dgn);
+            }
+        } else {
+            kept.push_back(o);
+        }
+    }
     return kept;
 }
 
-// Greedy "take what fits, skip what commutes": selects indices of `ops` (in order)
-// whose non-diagonal target bits fit in `cap` bits on top of `base_bits`.
-// Returns the chosen bit set; `taken` gets the selected indices, `rest` the others.
-static uint64_t greedy_group(const std::vector<CanonOp>& ops, const std::vector<int>& cand, uint64_t base_bits,
-                             uint64_t allowed_bits, int cap, std::vector<int>& taken, std::vector<int>& rest) {
+// ---- step 2/3: grouping -----------------------------------------------------
+// Greedy "take what fits, skip what commutes": selects indices of `ops` (in order) whose
+// non-diagonal target bits fit in `cap` more bits on top of `base_bits`, at most `max_take` ops.
+static uint64_t greedy_group(const std::vector<POp>& ops, const std::vector<int>& cand, uint64_t base_bits,
+                             uint64_t allowed_bits, int cap, size_t max_take, std::vector<int>& taken, std::vector<int>& rest) {
     uint64_t bits = base_bits, blocked_nd = 0, blocked_d = 0;
     int room = cap;
     taken.clear();
     rest.clear();
     for (int idx : cand) {
-        const CanonOp& c = ops[idx];
+        const POp& c = ops[idx];
         const uint64_t nd = nd_bits(c), dd = d_bits(c);
         const bool conflict = (nd & (blocked_nd | blocked_d)) || (dd & blocked_nd);
         const uint64_t need = nd & ~bits;
-        const bool placeable = (need & ~allowed_bits) == 0 && popc(need) <= room;
+        const bool placeable = (need & ~allowed_bits) == 0 && popc(need) <= room && taken.size() < max_take;
         if (!conflict && placeable) {
             bits |= need;
             room -= popc(need);
@@ -183,11 +394,9 @@ static uint64_t greedy_group(const std::vector<CanonOp>& ops, const std::vector<
 }
 
 // Grow a bit set one bit at a time, each time adding the candidate bit that lets a group take
-// the most ops from the head of `cand` (ops whose target lies on a chosen non-lane bit weigh
-// more: lane-only and diagonal ops fit any group).
-static uint64_t choose_bits(const std::vector<CanonOp>& ops, const std::vector<int>& cand, uint64_t base, uint64_t pool_limit,
-                            int count, int n) {
-    const uint64_t lane_mask = (1ull << kLaneBits) - 1ull;
+// the most ops from the head of `cand`.
+static uint64_t choose_bits(const std::vector<POp>& ops, const std::vector<int>& cand, uint64_t base, uint64_t pool_limit,
+                            int count, int n, size_t max_take) {
     const size_t kScore = std::min<size_t>(cand.size(), 768);
     std::vector<int> head(cand.begin(), cand.begin() + kScore), t2, r2;
     uint64_t chosen = base, pool = 0;
@@ -198,9 +407,9 @@ static uint64_t choose_bits(const std::vector<CanonOp>& ops, const std::vector<i
         size_t best = 0;
         for (int b = 0; b < n; ++b) {
             if (!(pool >> b & 1ull)) continue;
-            greedy_group(ops, head, chosen | (1ull << b), chosen | (1ull << b), 0, t2, r2);
+            greedy_group(ops, head, chosen | (1ull << b), chosen | (1ull << b), 0, max_take, t2, r2);
             size_t gain = 0;
-            for (int idx : t2) gain += (nd_bits(ops[idx]) & ~lane_mask) ? 4 : 1;
+            for (int idx : t2) gain += (nd_bits(ops[idx]) & ~base) ? 4 : 1;
             if (best_bit < 0 || gain > best) { best = gain; best_bit = b; }
         }
         if (best_bit < 0) break;
@@ -210,13 +419,251 @@ static uint64_t choose_bits(const std::vector<CanonOp>& ops, const std::vector<i
     return chosen;
 }
 
+// A layout of the T tile-local index bits: 5 register bits, the rest thread bits (ascending).
+struct Layout {
+    int T = 0;
+    int rpos[kRegBits];              // local position of register bit i
+    int tpos[kMaxThreadBits];        // local position of threadIdx bit j
+    int reg_of[16], thr_of[16];      // inverse maps (-1 if the position is of the other kind)
+    bool same(const Layout& o) const { return std::memcmp(rpos, o.rpos, sizeof rpos) == 0; }
+};
+static Layout make_layout(int T, uint32_t reg_positions) {
+    Layout L;
+    L.T = T;
+    int ri = 0, ti = 0;
+    for (int j = 0; j < 16; ++j) L.reg_of[j] = L.thr_of[j] = -1;
+    for (int j = 0; j < T; ++j) {
+        if (reg_positions >> j & 1u) { L.reg_of[j] = ri; L.rpos[ri++] = j; }
+        else { L.thr_of[j] = ti; L.tpos[ti++] = j; }
+    }
+    return L;
+}
+
+static int rank4(const uint32_t* v) {   // rank over GF(2) of four 4-bit vectors
+    uint32_t basis[4] = {0, 0, 0, 0};
+    int r = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t x = v[i] & 15u;
+        for (int b = 3; b >= 0 && x; --b) {
+            if (!(x >> b & 1u)) continue;
+            if (!basis[b]) { basis[b] = x; ++r; x = 0; break; }
+            x ^= basis[b];
+        }
+    }
+    return r;
+}
+
+// XOR swizzle for the re-split A -> B: slot(L) = L ^ XOR_{h >= 4, bit h of L} col[h], col[h] < 16.
+// 64-bit shared accesses are served per half-warp: the four low threadIdx bits of each layout must
+// map to four independent vectors in the low 4 slot bits.
+static void choose_swizzle(const Layout& A, const Layout& B, uint32_t* col) {
+    const int T = A.T;
+    for (int h = 0; h < 16; ++h) col[h] = 0;
+    auto ok = [&](const Layout& L) {
+        uint32_t v[4];
+        for (int j = 0; j < 4; ++j) {
+            const int p = L.tpos[j];
+            v[j] = (p < 4) ? (1u << p) : col[p];
+        }
+        return rank4(v) == 4;
+    };
+    if (ok(A) && ok(B)) return;
+    uint32_t free_pos = 0;
+    for (int j = 0; j < 4; ++j) {
+        if (A.tpos[j] >= 4) free_pos |= 1u << A.tpos[j];
+        if (B.tpos[j] >= 4) free_pos |= 1u << B.tpos[j];
+    }
+    uint64_t lcg = 0x9E3779B97F4A7C15ull ^ ((uint64_t)free_pos << 17);
+    for (int it = 0; it < 20000; ++it) {
+        for (int h = 4; h < T; ++h) {
+            if (!(free_pos >> h & 1u)) continue;
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            col[h] = (uint32_t)(lcg >> 60) & 15u;
+        }
+        if (ok(A) && ok(B)) return;
+    }
+    for (int h = 0; h < 16; ++h) col[h] = 0;   // give up: correct but conflicted
+}
+
+static void fill_cols(const Layout& L, const uint32_t* col, uint16_t* tcol, uint16_t* rcol) {
+    auto slot = [&](int p) { return (uint16_t)((1u << p) ^ (p >= 4 ? col[p] : 0u)); };
+    for (int j = 0; j < kMaxThreadBits; ++j) tcol[j] = (j < L.T - kRegBits) ? slot(L.tpos[j]) : 0;
+    for (int i = 0; i < kRegBits; ++i) rcol[i] = slot(L.rpos[i]);
+}
+
+// ---- step 4: emission -------------------------------------------------------
+struct Emitter {
+    int n, T;
+    uint64_t tile;                 // global bits of the tile
+    int local_of_bit[64];          // global bit -> tile-local position (-1 outside)
+    int block_bit[64];             // global bit outside the tile -> bit of the tile number
+    const Layout* L = nullptr;
+    std::vector<TileOp>* out = nullptr;
+
+    // Split a selection (mask, value) over global bits into register / thread / block parts.
+    // Returns false if the selection is empty for structural reasons (never).
+    void select(uint64_t mask, uint64_t val, uint32_t& rk_mask, uint32_t& rk_val, TileOp& t) const {
+        rk_mask = rk_val = 0;
+        for (int b = 0; b < n; ++b) {
+            if (!(mask >> b & 1ull)) continue;
+            const uint32_t v = (uint32_t)((val >> b) & 1ull);
+            const int j = local_of_bit[b];
+            if (j < 0) {
+                t.b_mask |= 1u << block_bit[b];
+                t.b_val |= v << block_bit[b];
+            } else if (L->reg_of[j] >= 0) {
+                rk_mask |= 1u << L->reg_of[j];
+                rk_val |= v << L->reg_of[j];
+            } else {
+                t.t_mask |= (uint16_t)(1u << L->thr_of[j]);
+                t.t_val |= (uint16_t)(v << L->thr_of[j]);
+            }
+        }
+    }
+    static uint32_t pair_mask(int tk, uint32_t rk_mask, uint32_t rk_val) {
+        uint32_t pairs = 0;
+        for (int pr = 0; pr < kPairs; ++pr) {
+            const uint32_t k0 = ((pr >> tk) << (tk + 1)) | (pr & ((1 << tk) - 1));
+            if ((k0 & rk_mask) == rk_val) pairs |= 1u << pr;
+        }
+        return pairs;
+    }
+    void emit_matrix(const cd* M, int tk, uint64_t cm, uint64_t cv) const {
+        if (mat_is_identity(M)) return;
+        TileOp t;
+        std::memset(&t, 0, sizeof t);
+        const Decomp d = decompose(M);
+        t.kind = (uint8_t)d.kind;
+        t.tk = (uint8_t)tk;
+        for (int i = 0; i < 8; ++i) t.a[i] = d.c[i];
+        uint32_t rm, rv;
+        select(cm, cv, rm, rv, t);
+        t.mask = pair_mask(tk, rm, rv);
+        if (t.mask) out->push_back(t);
+    }
+    void emit_phase(cd f, uint64_t sm, uint64_t sv) const {
+        if (z0(f - 1.0)) return;
+        TileOp t;
+        std::memset(&t, 0, sizeof t);
+        t.kind = TK_PHASE;
+        t.a[0] = (float)f.real();
+        t.a[1] = (float)f.imag();
+        uint32_t rm, rv;
+        select(sm, sv, rm, rv, t);
+        uint32_t act = 0;
+        for (uint32_t k = 0; k < (uint32_t)kRegs; ++k)
+            if ((k & rm) == rv) act |= 1u << k;
+        t.mask = act;
+        if (act) out->push_back(t);
+    }
+    // Bring two decompositions to one kind (for a per-thread coefficient select); false if impossible cheaply.
+    static bool common_kind(const cd* M0, const cd* M1, Decomp& d0, Decomp& d1) {
+        d0 = decompose(M0);
+        d1 = decompose(M1);
+        auto promote = [](Decomp& d, int kind) {
+            if (d.kind == kind) return true;
+            if ((d.kind == TK_SHR && kind == TK_SHR_P) || (d.kind == TK_SHI && kind == TK_SHI_P)) {
+                d.kind = kind; d.c[3] = 1.f; d.c[4] = 1.f; d.cost = 5;
+                return true;
+            }
+            return false;
+        };
+        auto is_id = [](const cd* M) { return mat_is_identity(M); };
+        // the identity fits every shear family: all coefficients zero
+        auto as_identity = [](Decomp& d, int kind) {
+            d = Decomp();
+            d.kind = kind;
+            d.c[3] = d.c[4] = 1.f;
+            d.cost = (kind == TK_SHR || kind == TK_SHI) ? 3 : 5;
+        };
+        if (is_id(M0) && d1.kind <= TK_SHI_P) { as_identity(d0, d1.kind); return true; }
+        if (is_id(M1) && d0.kind <= TK_SHI_P) { as_identity(d1, d0.kind); return true; }
+        if (d0.kind == d1.kind && d0.kind != TK_GEN) return true;
+        if (d0.kind > TK_SHI_Q || d1.kind > TK_SHI_Q) return false;
+        const int fam0 = (d0.kind == TK_SHR || d0.kind == TK_SHR_P) ? 0 : (d0.kind == TK_SHI || d0.kind == TK_SHI_P) ? 1 : 2;
+        const int fam1 = (d1.kind == TK_SHR || d1.kind == TK_SHR_P) ? 0 : (d1.kind == TK_SHI || d1.kind == TK_SHI_P) ? 1 : 2;
+        if (fam0 == fam1 && fam0 < 2) {
+            const int k = fam0 == 0 ? TK_SHR_P : TK_SHI_P;
+            return promote(d0, k) && promote(d1, k);
+        }
+        return false;
+    }
+    void emit(const POp& o, cd& pass_scale) const {
+        const uint64_t tb = 1ull << o.p;
+        if (o.diag) {
+            const cd d0 = o.m[0][0], d1 = o.m[0][3];
+            if (z0(d0 - 1.0)) {
+                emit_phase(d1, o.cmask | tb, o.cval | tb);
+            } else if (o.cmask == 0) {
+                // diag(d0, d1) = d0 * diag(1, d1/d0): d0 goes to the pass-wide scale
+                pass_scale *= d0;
+                emit_phase(d1 / d0, tb, tb);
+            } else {
+                emit_phase(d0, o.cmask | tb, o.cval);
+                emit_phase(d1, o.cmask | tb, o.cval | tb);
+            }
+            return;
+        }
+        const int tk = L->reg_of[local_of_bit[o.p]];
+        if (o.mux < 0) {
+            if (o.cmask == 0) {
+                // a common factor of the prescale (-1, or +-i for the AXLIKE family) is a global
+                // phase: it goes to the pass-wide scale and the op loses its prescale
+                const Decomp d = decompose(o.m[0]);
+                if ((d.kind == TK_SHR_P || d.kind == TK_SHI_P || d.kind == TK_SHI_Q) && d.c[3] == d.c[4]) {
+                    pass_scale *= (d.kind == TK_SHI_Q) ? cd(0.0, d.c[3]) : cd(d.c[3], 0.0);
+                    TileOp t;
+                    std::memset(&t, 0, sizeof t);
+                    t.kind = (uint8_t)(d.kind == TK_SHR_P ? TK_SHR : TK_SHI);
+                    t.tk = (uint8_t)tk;
+                    t.mask = 0xffffu;
+                    for (int i = 0; i < 3; ++i) t.a[i] = d.c[i];
+                    out->push_back(t);
+                    return;
+                }
+            }
+            emit_matrix(o.m[0], tk, o.cmask, o.cval);
+            return;
+        }
+        const uint64_t mb = 1ull << o.mux;
+        const int mj = local_of_bit[o.mux];
+        const bool lane_mux = mj >= 0 && L->thr_of[mj] >= 0 && L->thr_of[mj] < kLaneBits;
+        if (lane_mux && o.cmask == 0) {
+            // the control is a lane bit: one op, each thread picks its coefficient set
+            Decomp d0, d1;
+            if (common_kind(o.m[0], o.m[1], d0, d1) && d0.cost <= mat_cost(o.m[0]) + mat_cost(o.m[1])) {
+                TileOp t;
+                std::memset(&t, 0, sizeof t);
+                t.kind = (uint8_t)d1.kind;
+                t.tk = (uint8_t)tk;
+                t.flags = TF_MUX;
+                t.mask = 0xffffu;
+                t.t_mask = (uint16_t)(1u << L->thr_of[mj]);
+                t.t_val = t.t_mask;
+                for (int i = 0; i < 8; ++i) { t.a[i] = d1.c[i]; t.b[i] = d0.c[i]; }
+                out->push_back(t);
+                return;
+            }
+        }
+        // control on a register bit (pair subsets), a warp bit or a bit outside the tile (uniform predicates)
+        emit_matrix(o.m[0], tk, o.cmask | mb, o.cval);
+        emit_matrix(o.m[1], tk, o.cmask | mb, o.cval | mb);
+    }
+};
+
 static int build_fused(aqs_plan_s* p) {
     const int n = p->n;
-    const int T = std::min(n, kMaxTileBits);
+    int T = std::min(n, 12);
+    if (const char* e = std::getenv("AQS_TILE_BITS")) {
+        const int t = std::atoi(e);
+        if (t >= kMinTileBits && t <= kMaxTileBits) T = std::min(n, t);
+    }
+    const int TB = T - kRegBits;
     const uint64_t all_bits = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-    const uint64_t lane_mask = (1ull << kLaneBits) - 1ull;
+    const uint64_t low_mask = (1ull << kLaneBits) - 1ull;
+    const size_t kMaxTake = kOpsLarge / 2;     // every planner op emits at most two tile ops
 
-    std::vector<CanonOp> ops = simplify(n, p->ops);
+    std::vector<POp> ops = simplify(n, p->ops);
     // Sliding window over the op stream: a pass looks at the ops deferred by earlier passes plus
     // the next kWindow ops, so planning is O(passes * window) even for million-op circuits
     // (Grover-26 with 6433 iterations lowers to ~1e6 ops).
@@ -226,186 +673,188 @@ static int build_fused(aqs_plan_s* p) {
     while (true) {
         while (cand.size() < kWindow && next < ops.size()) cand.push_back((int)next++);
         if (cand.empty()) break;
-        // Tile choice.  Plain first-come filling scatters the tile over whatever targets come
-        // first; for nearest-neighbour circuits a better set exists.  Grow the tile one bit at a
-        // time, each time adding the bit that lets the pass take the most ops from the head of
-        // the window (skipped for huge op lists, where planning time matters more).
+        // Tile choice: grow the tile one bit at a time, each time adding the bit that lets the
+        // pass take the most ops from the head of the window (skipped for huge op lists, where
+        // planning time matters more).
         uint64_t tile;
         if (ops.size() <= 60000) {
-            const uint64_t chosen = choose_bits(ops, cand, lane_mask, all_bits, T - kLaneBits, n);
-            tile = greedy_group(ops, cand, chosen, chosen, 0, taken, rest);
+            const uint64_t chosen = choose_bits(ops, cand, low_mask, all_bits, T - kLaneBits, n, kMaxTake);
+            tile = greedy_group(ops, cand, chosen, chosen, 0, kMaxTake, taken, rest);
         } else {
-            tile = greedy_group(ops, cand, lane_mask, all_bits, T - kLaneBits, taken, rest);
+            tile = greedy_group(ops, cand, low_mask, all_bits, T - kLaneBits, kMaxTake, taken, rest);
         }
         if (taken.empty()) return fail(AQS_ERR_STATE, "fusion planner made no progress");
         // pad the tile to exactly T bits with the lowest unused positions
         for (int b = 0; b < n && popc(tile) < T; ++b) tile |= 1ull << b;
 
         FusedPass fp;
-        std::complex<double> pass_scale(1.0, 0.0);
-        fp.warps_log2 = T - kMinTileBits;
+        fp.T = T;
         fp.n_tiles = 1ull << (n - T);
-        std::memset(&fp.args, 0, sizeof fp.args);
-        fp.args.tile_bits = (uint32_t)T;
-        fp.args.tile.n = 0;
-        int local_of_bit[64];
-        for (int b = 0; b < 64; ++b) local_of_bit[b] = -1;
-        for (int b = 0; b < n; ++b)
+        Emitter em;
+        em.n = n; em.T = T; em.tile = tile;
+        em.out = &fp.ops;
+        fp.tile.n = 0;
+        int nb = 0;
+        for (int b = 0; b < 64; ++b) em.local_of_bit[b] = em.block_bit[b] = -1;
+        for (int b = 0; b < n; ++b) {
             if (tile >> b & 1ull) {
-                local_of_bit[b] = fp.args.tile.n;
-                fp.args.tile.pos[fp.args.tile.n++] = (uint8_t)b;
+                em.local_of_bit[b] = fp.tile.n;
+                fp.tile.pos[fp.tile.n++] = (uint8_t)b;
+            } else {
+                em.block_bit[b] = nb++;
             }
+        }
+        uint64_t global_of_local[16];
+        for (int j = 0; j < T; ++j) global_of_local[j] = 1ull << fp.tile.pos[j];
 
-        // segments: same greedy with 4 register bits among the non-lane tile bits
+        // segments: the same greedy with 5 register bits among ALL tile bits
+        std::vector<Layout> layouts;
+        std::vector<std::pair<uint32_t, uint32_t>> ranges;   // (first_op, n_ops) per layout
         std::vector<int> seg_cand = taken, seg_taken, seg_rest;
-        const uint64_t reg_allowed = tile & ~lane_mask;
+        cd pass_scale(1.0, 0.0);
+        auto default_regs = [&](uint32_t want) {
+            // complete `want` (a set of local positions) to 5 register positions, highest free first
+            for (int j = T - 1; j >= 0 && popc(want) < kRegBits; --j)
+                if (!(want >> j & 1u)) want |= 1u << j;
+            return want;
+        };
+        std::vector<int> unplaced;
         while (!seg_cand.empty()) {
-            // lane-bit targets are always placeable: treat lane bits as already present
-            uint64_t chosen = greedy_group(ops, seg_cand, lane_mask, reg_allowed, kRegBits, seg_taken, seg_rest);
+            if ((int)layouts.size() >= kMaxSegs - 2) { unplaced = seg_cand; break; }
+            uint64_t chosen = greedy_group(ops, seg_cand, 0, tile, kRegBits, kMaxTake, seg_taken, seg_rest);
             if (seg_taken.empty()) return fail(AQS_ERR_STATE, "fusion planner made no progress (segment)");
-            uint64_t regs = chosen & ~lane_mask;
-            for (int b = kLaneBits; b < n && popc(regs) < kRegBits; ++b)
-                if ((reg_allowed >> b & 1ull) && !(regs >> b & 1ull)) regs |= 1ull << b;
-
-            TileSeg sg;
-            std::memset(&sg, 0, sizeof sg);
-            int reg_index_of_local[16];
-            for (int j = 0; j < 16; ++j) reg_index_of_local[j] = -1;
-            int ri = 0, wi = 0;
-            for (int j = kLaneBits; j < T; ++j) {
-                const int b = fp.args.tile.pos[j];
-                if (regs >> b & 1ull) { reg_index_of_local[j] = ri; sg.R[ri++] = (uint8_t)j; }
-                else sg.W[wi++] = (uint8_t)j;
+            uint32_t regs = 0;
+            for (int b = 0; b < n; ++b)
+                if (chosen >> b & 1ull) regs |= 1u << em.local_of_bit[b];
+            // an all-diagonal segment keeps the previous layout
+            if (regs == 0 && !layouts.empty()) {
+                for (int i = 0; i < kRegBits; ++i) regs |= 1u << layouts.back().rpos[i];
             }
-            sg.first_op = (uint32_t)fp.ops.size();
-            // emits one tile op; (cm, cv) are the complete control mask/value in global bit positions
-            auto emit = [&](const CanonOp& c, uint8_t mode, int tk, uint64_t cm, uint64_t cv, const float2 m[4]) {
-                TileOp t;
-                std::memset(&t, 0, sizeof t);
-                t.mode = mode;
-                t.tk = (uint8_t)tk;
-                for (int i = 0; i < 4; ++i) t.m[i] = m[i];
-                t.g_mask = cm & ~tile;
-                t.g_val = cv & ~tile;
-                uint32_t rk_mask = 0, rk_val = 0;
-                for (int b = 0; b < n; ++b) {
-                    if (!(cm & tile & (1ull << b))) continue;
-                    const int j = local_of_bit[b];
-                    const uint32_t v = (cv >> b) & 1ull;
-                    if (reg_index_of_local[j] >= 0) {
-                        rk_mask |= 1u << reg_index_of_local[j];
-                        rk_val |= v << reg_index_of_local[j];
-                    } else {
-                        t.tl_mask |= (uint16_t)(1u << j);
-                        t.tl_val |= (uint16_t)(v << j);
-                    }
-                }
-                uint32_t act = 0;   // registers enabled by the controls that live on register bits
-                for (uint32_t k = 0; k < (uint32_t)kRegs; ++k)
-                    if ((k & rk_mask) == rk_val) act |= 1u << k;
-                if (mode <= TM_REG_PERM) {
-                    uint32_t pairs = 0;
-                    for (int pr = 0; pr < kRegs / 2; ++pr) {
-                        const int k0 = ((pr >> tk) << (tk + 1)) | (pr & ((1 << tk) - 1));
-                        if (act >> k0 & 1u) pairs |= 1u << pr;
-                    }
-                    t.amp_mask = (uint16_t)pairs;
-                } else {
-                    t.amp_mask = (uint16_t)act;
-                }
-                (void)c;
-                fp.ops.push_back(t);
-            };
-            for (int idx : seg_taken) {
-                const CanonOp& c = ops[idx];
-                if (c.kind == AQS_OP_DIAG) {
-                    // every diagonal becomes "one factor on a selected subset"
-                    const uint64_t tb = 1ull << c.p;
-                    float2 one[4] = {make_float2(1.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(1.f, 0.f)};
-                    if (c.d0_one) {
-                        one[0] = c.m[3];
-                        emit(c, TM_PHASE, 0, c.cmask | tb, c.cval | tb, one);
-                    } else if (c.cmask == 0) {
-                        // diag(d0, d1) = d0 * diag(1, d1/d0): d0 goes to the pass-wide scale
-                        const std::complex<double> d0(c.m[0].x, c.m[0].y), d1(c.m[3].x, c.m[3].y);
-                        pass_scale *= d0;
-                        const std::complex<double> r = d1 / d0;
-                        one[0] = make_float2((float)r.real(), (float)r.imag());
-                        emit(c, TM_PHASE, 0, tb, tb, one);
-                    } else {
-                        one[0] = c.m[0];
-                        emit(c, TM_PHASE, 0, c.cmask | tb, c.cval, one);        // target bit 0
-                        one[0] = c.m[3];
-                        emit(c, TM_PHASE, 0, c.cmask | tb, c.cval | tb, one);   // target bit 1
-                    }
-                    continue;
-                }
-                const int j = local_of_bit[c.p];
-                const bool perm = (c.kind == AQS_OP_X);
-                float2 m[4];
-                full_matrix(c, m);
-                if (j < kLaneBits) {
-                    emit(c, perm ? TM_LANE_PERM : TM_LANE_GEN, j, c.cmask, c.cval, m);
-                } else {
-                    uint8_t mode = TM_REG_GEN;
-                    if (perm) mode = TM_REG_PERM;
-                    else if (m[0].y == 0.f && m[1].y == 0.f && m[2].y == 0.f && m[3].y == 0.f) mode = TM_REG_REAL;
-                    else if (m[0].y == 0.f && m[3].y == 0.f && m[1].x == 0.f && m[2].x == 0.f) mode = TM_REG_XLIKE;
-                    emit(c, mode, reg_index_of_local[j], c.cmask, c.cval, m);
-                }
+            regs = default_regs(regs);
+            Layout L = make_layout(T, regs);
+            const uint32_t first = (uint32_t)fp.ops.size();
+            em.L = &L;
+            for (int idx : seg_taken) em.emit(ops[idx], pass_scale);
+            const uint32_t cnt = (uint32_t)fp.ops.size() - first;
+            if (!layouts.empty() && layouts.back().same(L)) {
+                ranges.back().second += cnt;
+            } else {
+                layouts.push_back(L);
+                ranges.push_back({first, cnt});
             }
-            sg.n_ops = (uint32_t)fp.ops.size() - sg.first_op;
-            fp.segs.push_back(sg);
             seg_cand.swap(seg_rest);
         }
-        fp.args.scale = make_float2((float)pass_scale.real(), (float)pass_scale.imag());
-        fp.args.has_scale = (pass_scale != std::complex<double>(1.0, 0.0)) ? 1u : 0u;
+        if (fp.ops.size() > (size_t)kOpsLarge) return fail(AQS_ERR_STATE, "fusion planner overflowed a pass");
+        if (!unplaced.empty()) {
+            // the pass ran out of segments: give the remaining ops back, in program order
+            std::vector<int> merged(unplaced.size() + rest.size());
+            std::merge(unplaced.begin(), unplaced.end(), rest.begin(), rest.end(), merged.begin());
+            rest.swap(merged);
+        }
+        // entry / exit layouts must keep the low five index bits on the lanes (coalesced global access)
+        auto io_ok = [&](const Layout& L) {
+            for (int i = 0; i < kRegBits; ++i)
+                if (L.rpos[i] < kLaneBits) return false;
+            return true;
+        };
+        auto io_layout_for = [&](const Layout& L) {
+            uint32_t keep = 0;
+            for (int i = 0; i < kRegBits; ++i)
+                if (L.rpos[i] >= kLaneBits) keep |= 1u << L.rpos[i];
+            uint32_t want = keep;
+            for (int j = T - 1; j >= kLaneBits && popc(want) < kRegBits; --j)
+                if (!(want >> j & 1u)) want |= 1u << j;
+            return make_layout(T, want);
+        };
+        if (!io_ok(layouts.front())) {
+            layouts.insert(layouts.begin(), io_layout_for(layouts.front()));
+            ranges.insert(ranges.begin(), {0u, 0u});
+        }
+        if (!io_ok(layouts.back())) {
+            layouts.push_back(io_layout_for(layouts.back()));
+            ranges.push_back({(uint32_t)fp.ops.size(), 0u});
+        }
+        for (size_t s = 0; s < layouts.size(); ++s) {
+            TileSeg sg;
+            std::memset(&sg, 0, sizeof sg);
+            sg.first_op = (uint16_t)ranges[s].first;
+            sg.n_ops = (uint16_t)ranges[s].second;
+            if (s > 0) {
+                uint32_t col[16];
+                choose_swizzle(layouts[s - 1], layouts[s], col);
+                fill_cols(layouts[s - 1], col, sg.wr_tcol, sg.wr_rcol);
+                fill_cols(layouts[s], col, sg.rd_tcol, sg.rd_rcol);
+                sg.resplit = 1;
+            }
+            fp.segs.push_back(sg);
+        }
+        auto io_offsets = [&](const Layout& L, uint64_t* toff, uint64_t* roff) {
+            for (int j = 0; j < kMaxThreadBits; ++j) toff[j] = (j < TB) ? global_of_local[L.tpos[j]] : 0;
+            for (int i = 0; i < kRegBits; ++i) roff[i] = global_of_local[L.rpos[i]];
+        };
+        io_offsets(layouts.front(), fp.ld_toff, fp.ld_roff);
+        io_offsets(layouts.back(), fp.st_toff, fp.st_roff);
+        fp.scale = make_float2((float)pass_scale.real(), (float)pass_scale.imag());
+        fp.has_scale = (pass_scale != cd(1.0, 0.0));
         p->passes.push_back(std::move(fp));
         cand.swap(rest);
     }
-
     return AQS_OK;
 }
 
-// Device copy of every descriptor, made on first use so that plans can be built
-// (and inspected) without a GPU.
-static int ensure_uploaded(aqs_plan_s* p) {
-    if (p->arena || p->passes.empty()) return AQS_OK;
-    auto pad = [](size_t b) { return ((b + 255) / 256) * 256; };
-    size_t bytes = 0;
-    for (auto& fp : p->passes) bytes += pad(fp.segs.size() * sizeof(TileSeg)) + pad(fp.ops.size() * sizeof(TileOp));
-    std::vector<char> host(bytes);
-    cudaError_t e = pool_alloc(&p->arena, bytes);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(plan arena)", __LINE__);
-    p->arena_bytes = bytes;
-    size_t off = 0;
-    for (auto& fp : p->passes) {
-        fp.args.segs = reinterpret_cast<const TileSeg*>((char*)p->arena + off);
-        std::memcpy(host.data() + off, fp.segs.data(), fp.segs.size() * sizeof(TileSeg));
-        off += pad(fp.segs.size() * sizeof(TileSeg));
-        fp.args.ops = reinterpret_cast<const TileOp*>((char*)p->arena + off);
-        std::memcpy(host.data() + off, fp.ops.data(), fp.ops.size() * sizeof(TileOp));
-        off += pad(fp.ops.size() * sizeof(TileOp));
-        fp.args.n_segs = (uint32_t)fp.segs.size();
+template <int CAP>
+static void fill_params(PassParams<CAP>& P, float2* state, const FusedPass& fp) {
+    P.state = state;
+    P.n_segs = (uint32_t)fp.segs.size();
+    P.n_ops = (uint32_t)fp.ops.size();
+    P.scale = fp.scale;
+    P.has_scale = fp.has_scale ? 1u : 0u;
+    P.tile_bits = (uint32_t)fp.T;
+    std::memcpy(P.ld_toff, fp.ld_toff, sizeof P.ld_toff);
+    std::memcpy(P.ld_roff, fp.ld_roff, sizeof P.ld_roff);
+    std::memcpy(P.st_toff, fp.st_toff, sizeof P.st_toff);
+    std::memcpy(P.st_roff, fp.st_roff, sizeof P.st_roff);
+    P.tile = fp.tile;
+    std::memcpy(P.segs, fp.segs.data(), fp.segs.size() * sizeof(TileSeg));
+    std::memcpy(P.ops, fp.ops.data(), fp.ops.size() * sizeof(TileOp));
+}
+
+template <int T, int CAP>
+static cudaError_t launch_tile(float2* state, const FusedPass& fp, cudaStream_t st) {
+    static PassParams<CAP> P;            // zero-initialised once; only the used prefix is rewritten
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    fill_params(P, state, fp);
+    constexpr size_t smem = sizeof(float2) << T;
+    k_tile2<T, CAP><<<(unsigned)fp.n_tiles, 1 << (T - kRegBits), smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <int CAP>
+static cudaError_t launch_tile_t(float2* state, const FusedPass& fp, cudaStream_t st) {
+    switch (fp.T) {
+        case 10: return launch_tile<10, CAP>(state, fp, st);
+        case 11: return launch_tile<11, CAP>(state, fp, st);
+        case 12: return launch_tile<12, CAP>(state, fp, st);
+        default: return launch_tile<13, CAP>(state, fp, st);
     }
-    e = cudaMemcpy(p->arena, host.data(), bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(plan arena)", __LINE__);
-    count_h2d(bytes);
-    return AQS_OK;
 }
 
 static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st) {
-    TileArgs a = fp.args;
-    a.state = state;
     if (fp.n_tiles > 0x7fffffffull) return fail(AQS_ERR_INVALID, "grid too large");
-    const unsigned grid = (unsigned)fp.n_tiles;
-    switch (fp.warps_log2) {
-        case 0: k_tile<0><<<grid, 32, 0, st>>>(a); break;
-        case 1: k_tile<1><<<grid, 64, 0, st>>>(a); break;
-        case 2: k_tile<2><<<grid, 128, 0, st>>>(a); break;
-        default: k_tile<3><<<grid, 256, 0, st>>>(a); break;
-    }
+    const cudaError_t e = (fp.ops.size() <= (size_t)kOpsSmall) ? launch_tile_t<kOpsSmall>(state, fp, st)
+                                                               : launch_tile_t<kOpsLarge>(state, fp, st);
+    if (e != cudaSuccess) return fail_cuda(e, "tile kernel launch", __LINE__);
     count_launch(1);
+    return AQS_OK;
+}
+
+int fused_init() {
+    // 64 KiB of dynamic shared memory for the 13-bit tile needs the opt-in
+    cudaError_t e = cudaFuncSetAttribute(k_tile2<13, kOpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) << 13));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tile2<13, kOpsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) << 13));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tile kernel)", __LINE__);
     return AQS_OK;
 }
 
@@ -440,22 +889,31 @@ int aqs_plan_build(int n, const aqs_op* ops, uint64_t n_ops, uint32_t flags, aqs
         if (rc) { aqs_plan_destroy(p); return rc; }
     }
     if (!p->passes.empty()) {
-        uint64_t single = 0;
         p->info.n_launches = p->passes.size();
         p->info.n_fused_passes = p->passes.size();
-        p->info.n_single_ops = single;
+        p->info.n_single_ops = 0;
         p->info.bytes_planned = 2.0 * 8.0 * std::ldexp(1.0, n) * (double)p->passes.size();
-        p->info.tile_bits = std::min(n, kMaxTileBits);
+        p->info.tile_bits = p->passes[0].T;
         if (std::getenv("AQS_PLAN_DUMP")) {
             size_t segs = 0, tops = 0;
             for (auto& fp : p->passes) { segs += fp.segs.size(); tops += fp.ops.size(); }
-            std::fprintf(stderr, "[aqs plan] n=%d ops=%llu -> %zu tile ops, %zu passes, %zu segments\n", n,
+            std::fprintf(stderr, "[aqs plan] n=%d ops=%llu -> %zu tile ops, %zu passes, %zu layouts\n", n,
                          (unsigned long long)n_ops, tops, p->passes.size(), segs);
             if (std::atoi(std::getenv("AQS_PLAN_DUMP")) > 1)
                 for (size_t i = 0; i < p->passes.size(); ++i) {
                     auto& fp = p->passes[i];
-                    std::fprintf(stderr, "  pass %zu: %zu ops in %zu segments, tile bits", i, fp.ops.size(), fp.segs.size());
-                    for (int j = 0; j < fp.args.tile.n; ++j) std::fprintf(stderr, " %d", fp.args.tile.pos[j]);
+                    int km[16] = {0}, masked = 0, muxed = 0, cost = 0;
+                    for (auto& t : fp.ops) {
+                        km[t.kind & 15]++;
+                        const bool full = (t.kind == TK_PHASE) ? (t.mask == 0xffffffffu) : (t.mask == 0xffffu);
+                        masked += !full;
+                        muxed += (t.flags & TF_MUX) != 0;
+                        const int per = (t.kind == TK_SHR || t.kind == TK_SHI) ? 3 : (t.kind == TK_GEN ? 8 : ((t.kind == TK_PHASE || t.kind >= TK_PERM_R) ? 2 : 5));
+                        cost += per * popc(t.mask);
+                    }
+                    std::fprintf(stderr, "  pass %zu: %zu ops in %zu layouts [shr %d shr_p %d shi %d shi_p %d shi_q %d gen %d phase %d perm %d | masked %d mux %d | ~%d ffma2/thread], tile bits",
+                                 i, fp.ops.size(), fp.segs.size(), km[0], km[1], km[2], km[3], km[4], km[5], km[6], km[7] + km[8], masked, muxed, cost);
+                    for (int j = 0; j < fp.tile.n; ++j) std::fprintf(stderr, " %d", fp.tile.pos[j]);
                     std::fprintf(stderr, "\n");
                 }
         }
@@ -490,10 +948,6 @@ static int launch_all(aqs_state_t s, aqs_plan_t p) {
 int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
     if (!s || !p) return fail(AQS_ERR_INVALID, "null handle");
     if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
-    int up = ensure_uploaded(p);
-    if (up) return up;
-    p->last_stream = s->stream;
-    p->ran = true;
     if (p->flags & AQS_PLAN_GRAPH) {
         // launch-bound plans (small states, thousands of passes): replay one CUDA graph instead of
         // issuing every launch from the host.  The graph bakes in the state's buffer, so it is
@@ -531,11 +985,40 @@ int aqs_plan_get_info(aqs_plan_t p, aqs_plan_info* info) {
     return AQS_OK;
 }
 
+// Introspection for tests and tools: the exact launch descriptors of fused pass `index`, as
+// { uint32 tile_bits, uint32 n_segs, uint32 n_ops, uint32 has_scale, float2 scale, uint64 n_tiles,
+//   BitList tile, uint64 ld_toff[8], ld_roff[5], st_toff[8], st_roff[5], TileSeg segs[n_segs], TileOp ops[n_ops] }.
+// Returns the number of bytes the record needs in *needed; copies it when `cap` is large enough.
+int aqs_plan_export_pass(aqs_plan_t p, uint64_t index, void* buf, uint64_t cap, uint64_t* needed) {
+    if (!p || !needed) return fail(AQS_ERR_INVALID, "null argument");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    const FusedPass& fp = p->passes[index];
+    struct Head {
+        uint32_t tile_bits, n_segs, n_ops, has_scale;
+        float2 scale;
+        uint64_t n_tiles;
+        BitList tile;
+        uint64_t ld_toff[kMaxThreadBits], ld_roff[kRegBits], st_toff[kMaxThreadBits], st_roff[kRegBits];
+    } h;
+    std::memset(&h, 0, sizeof h);
+    h.tile_bits = (uint32_t)fp.T; h.n_segs = (uint32_t)fp.segs.size(); h.n_ops = (uint32_t)fp.ops.size();
+    h.has_scale = fp.has_scale; h.scale = fp.scale; h.n_tiles = fp.n_tiles; h.tile = fp.tile;
+    std::memcpy(h.ld_toff, fp.ld_toff, sizeof h.ld_toff); std::memcpy(h.ld_roff, fp.ld_roff, sizeof h.ld_roff);
+    std::memcpy(h.st_toff, fp.st_toff, sizeof h.st_toff); std::memcpy(h.st_roff, fp.st_roff, sizeof h.st_roff);
+    const uint64_t bytes = sizeof h + fp.segs.size() * sizeof(TileSeg) + fp.ops.size() * sizeof(TileOp);
+    *needed = bytes;
+    if (buf && cap >= bytes) {
+        char* o = (char*)buf;
+        std::memcpy(o, &h, sizeof h); o += sizeof h;
+        std::memcpy(o, fp.segs.data(), fp.segs.size() * sizeof(TileSeg)); o += fp.segs.size() * sizeof(TileSeg);
+        std::memcpy(o, fp.ops.data(), fp.ops.size() * sizeof(TileOp));
+    }
+    return AQS_OK;
+}
+
 int aqs_plan_destroy(aqs_plan_t p) {
     if (!p) return AQS_OK;
-    if (p->ran && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();   // kernels may still read the arena
     if (p->graph) cudaGraphExecDestroy(p->graph);
-    if (p->arena) pool_free(p->arena, p->arena_bytes);
     delete p;
     return AQS_OK;
 }

@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "aqs_state_create", "aqs_state_wrap", "aqs_state_destroy", "aqs_state_clone", "aqs_state_qubits", "aqs_state_set_basis",
     "aqs_state_set_product", "aqs_state_set_identity", "aqs_state_upload", "aqs_state_download",
     "aqs_state_get_amp", "aqs_state_device_ptr", "aqs_state_set_stream", "aqs_state_get_stream", "aqs_sync",
-    "aqs_apply_op", "aqs_apply_ops", "aqs_plan_build", "aqs_plan_run", "aqs_plan_get_info", "aqs_plan_destroy",
+    "aqs_apply_op", "aqs_apply_ops", "aqs_plan_build", "aqs_plan_run", "aqs_plan_get_info", "aqs_plan_destroy", "aqs_plan_export_pass",
     "aqs_norm2", "aqs_scale", "aqs_prob_fixed", "aqs_qubit_prob1", "aqs_probabilities", "aqs_collapse_qubit",
     "aqs_sample", "aqs_sample_fixed", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
@@ -81,6 +81,7 @@ def load():
         "aqs_sync": [vp], "aqs_apply_op": [vp, vp], "aqs_apply_ops": [vp, vp, u64],
         "aqs_plan_build": [i32, vp, u64, ctypes.c_uint32, P(vp)], "aqs_plan_run": [vp, vp],
         "aqs_plan_get_info": [vp, P(PlanInfo)], "aqs_plan_destroy": [vp],
+        "aqs_plan_export_pass": [vp, u64, vp, u64, P(u64)],
         "aqs_norm2": [vp, P(ctypes.c_double)], "aqs_scale": [vp, f32],
         "aqs_prob_fixed": [vp, u64, u64, P(u64)], "aqs_qubit_prob1": [vp, i32, P(ctypes.c_double)],
         "aqs_probabilities": [vp, vp, u64, u64], "aqs_collapse_qubit": [vp, i32, i32, f32],
@@ -176,6 +177,14 @@ class Plan:
         pi = PlanInfo()
         _check(load().aqs_plan_get_info(self._h, ctypes.byref(pi)))
         return {k: getattr(pi, k) for k, _ in PlanInfo._fields_}
+
+    def export_pass(self, index: int) -> bytes:
+        """Raw launch descriptors of fused pass `index` (tests/tile_emulator.py parses them)."""
+        need = ctypes.c_uint64()
+        _check(load().aqs_plan_export_pass(self._h, index, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        _check(load().aqs_plan_export_pass(self._h, index, buf, need.value, ctypes.byref(need)))
+        return buf.raw
 
     def close(self):
         if self._h:

@@ -146,6 +146,10 @@ int aqs_plan_build(int n_qubits, const aqs_op* ops, uint64_t n_ops, uint32_t fla
 int aqs_plan_run(aqs_state_t s, aqs_plan_t p);
 int aqs_plan_get_info(aqs_plan_t p, aqs_plan_info* info);
 int aqs_plan_destroy(aqs_plan_t p);
+/* Introspection (tests, tools): the launch descriptors of fused pass `index`, exactly as the tile
+ * kernel receives them (record layout: afquantumsim_b200/csrc/plan.cu).  *needed gets the record
+ * size; the record is copied when cap is large enough.  No reference counterpart. */
+int aqs_plan_export_pass(aqs_plan_t p, uint64_t index, void* buf, uint64_t cap, uint64_t* needed);
 
 /* ---- probabilities and measurement -----------------------------------------
  * Exact-sum contract: p_k = fl32(fl32(re*re)+fl32(im*im)),

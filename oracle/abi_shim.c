@@ -153,6 +153,10 @@ int aqs_plan_get_info(aqs_plan_t p, aqs_plan_info* info) {
     return AQS_OK;
 }
 int aqs_plan_destroy(aqs_plan_t p) { if (p) { free(p->ops); free(p); } return AQS_OK; }
+int aqs_plan_export_pass(aqs_plan_t p, uint64_t index, void* buf, uint64_t cap, uint64_t* needed) {
+    (void)p; (void)index; (void)buf; (void)cap; (void)needed;
+    return fail(AQS_ERR_INVALID, "the CPU stand-in has no fused passes");
+}
 
 int aqs_norm2(aqs_state_t s, double* out) { REQ(s && out, "null"); *out = orc_norm2(s->a, s->n); return AQS_OK; }
 int aqs_scale(aqs_state_t s, float f) { REQ(s, "null"); for (uint64_t r = 0; r < s->N; ++r) { s->a[r].re *= f; s->a[r].im *= f; } return AQS_OK; }

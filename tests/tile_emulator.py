@@ -1,0 +1,210 @@
+"""Test infrastructure: a numpy interpreter of the tile kernel's launch descriptors.
+
+`Plan.export_pass` returns the exact bytes a fused pass hands to `k_tile2`
+(afquantumsim_b200/csrc/tile_kernel.cuh: PassParams / TileSeg / TileOp).  This module
+re-executes them on the CPU with the kernel's semantics — layouts (register bits /
+thread bits), shared-memory swizzles, predicates, coefficient sets, in-place shears —
+so the planner can be checked against the oracle without a GPU, and so that a GPU
+mismatch can be pinned on the kernel rather than on the plan.  It is never imported by
+the package."""
+import ctypes
+
+import numpy as np
+
+K_LANE, K_REG, K_MAX_THREAD_BITS, K_MAX_BITS = 5, 5, 8, 38
+SHR, SHR_P, SHI, SHI_P, SHI_Q, GEN, PHASE, PERM_R, PERM_I = range(9)
+TF_MUX = 1
+
+
+class BitList(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("pos", ctypes.c_uint8 * K_MAX_BITS)]
+
+
+class Head(ctypes.Structure):
+    _fields_ = [("tile_bits", ctypes.c_uint32), ("n_segs", ctypes.c_uint32), ("n_ops", ctypes.c_uint32),
+                ("has_scale", ctypes.c_uint32), ("scale", ctypes.c_float * 2), ("n_tiles", ctypes.c_uint64),
+                ("tile", BitList),
+                ("ld_toff", ctypes.c_uint64 * K_MAX_THREAD_BITS), ("ld_roff", ctypes.c_uint64 * K_REG),
+                ("st_toff", ctypes.c_uint64 * K_MAX_THREAD_BITS), ("st_roff", ctypes.c_uint64 * K_REG)]
+
+
+class TileSeg(ctypes.Structure):
+    _fields_ = [("rd_tcol", ctypes.c_uint16 * K_MAX_THREAD_BITS), ("rd_rcol", ctypes.c_uint16 * K_REG),
+                ("wr_tcol", ctypes.c_uint16 * K_MAX_THREAD_BITS), ("wr_rcol", ctypes.c_uint16 * K_REG),
+                ("first_op", ctypes.c_uint16), ("n_ops", ctypes.c_uint16), ("resplit", ctypes.c_uint8),
+                ("pad", ctypes.c_uint8 * 7)]
+
+
+class TileOp(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint8), ("tk", ctypes.c_uint8), ("flags", ctypes.c_uint8), ("pad0", ctypes.c_uint8),
+                ("mask", ctypes.c_uint32), ("t_mask", ctypes.c_uint16), ("t_val", ctypes.c_uint16),
+                ("b_mask", ctypes.c_uint32), ("b_val", ctypes.c_uint32), ("pad1", ctypes.c_uint32 * 3),
+                ("a", ctypes.c_float * 8), ("b", ctypes.c_float * 8)]
+
+
+assert ctypes.sizeof(TileSeg) == 64 and ctypes.sizeof(TileOp) == 96
+
+
+def parse(raw: bytes):
+    head = Head.from_buffer_copy(raw)
+    off = ctypes.sizeof(Head)
+    segs = []
+    for _ in range(head.n_segs):
+        segs.append(TileSeg.from_buffer_copy(raw, off))
+        off += ctypes.sizeof(TileSeg)
+    ops = []
+    for _ in range(head.n_ops):
+        ops.append(TileOp.from_buffer_copy(raw, off))
+        off += ctypes.sizeof(TileOp)
+    assert off == len(raw)
+    return head, segs, ops
+
+
+def _xor_cols(bits, cols, nbits):
+    out = np.zeros_like(bits)
+    for j in range(nbits):
+        out ^= np.where((bits >> j) & 1, np.uint32(cols[j]), np.uint32(0)).astype(np.uint32)
+    return out
+
+
+def _sum_cols(bits, cols, nbits):
+    out = np.zeros(bits.shape, dtype=np.uint64)
+    for j in range(nbits):
+        out += np.where((bits >> j) & 1, np.uint64(cols[j]), np.uint64(0)).astype(np.uint64)
+    return out
+
+
+def deposit(j, positions):
+    """insert a zero bit at every listed position, lowest first (common.cuh deposit_zeros)"""
+    j = j.astype(np.uint64)
+    for p in positions:
+        lo = j & np.uint64((1 << p) - 1)
+        j = ((j >> np.uint64(p)) << np.uint64(p + 1)) | lo
+    return j
+
+
+def butterfly(kind, x, y, c):
+    """the kernel's in-place sequences, in float32 (tile_kernel.cuh butterfly<>)"""
+    f = np.float32
+    c = [f(v) for v in c]
+    if kind in (SHR, SHR_P):
+        if kind == SHR_P:
+            x = x * c[3]
+            y = y * c[4]
+        x = x + c[0] * y
+        y = y + c[1] * x
+        x = x + c[2] * y
+    elif kind in (SHI, SHI_P, SHI_Q):
+        j = np.complex64(1j)
+        if kind == SHI_P:
+            x = x * c[3]
+            y = y * c[4]
+        elif kind == SHI_Q:
+            x = x * (j * c[3])
+            y = y * (j * c[4])
+        x = x + (j * c[0]) * y
+        y = y + (j * c[1]) * x
+        x = x + (j * c[2]) * y
+    elif kind == PERM_R:
+        x, y = c[0] * y, c[1] * x
+    elif kind == PERM_I:
+        x, y = (np.complex64(1j) * c[0]) * y, (np.complex64(1j) * c[1]) * x
+    else:
+        m = [np.complex64(complex(c[2 * i], c[2 * i + 1])) for i in range(4)]
+        x, y = m[0] * x + m[1] * y, m[2] * x + m[3] * y
+    return x.astype(np.complex64), y.astype(np.complex64)
+
+
+def check_swizzle(seg, T, stats):
+    """every re-split must be a bijection and keep each half-warp's 64-bit accesses on 16 distinct bank pairs"""
+    TB = T - K_REG
+    tid = np.arange(1 << TB, dtype=np.uint32)
+    k = np.arange(32, dtype=np.uint32)
+    for tcol, rcol, what in ((seg.wr_tcol, seg.wr_rcol, "store"), (seg.rd_tcol, seg.rd_rcol, "load")):
+        slot = _xor_cols(tid, tcol, TB)[:, None] ^ _xor_cols(k, rcol, K_REG)[None, :]
+        assert slot.max() < (1 << T)
+        assert len(np.unique(slot)) == slot.size, f"{what} layout is not a bijection"
+        banks = (slot & 15).reshape(-1, 16, 32)      # half-warps x lanes x registers
+        worst = max(16 - len(np.unique(banks[h, :, r])) for h in range(0, banks.shape[0], max(1, banks.shape[0] // 8)) for r in (0, 31))
+        stats["conflicts"] = max(stats.get("conflicts", 0), worst)
+
+
+def run_pass(state: np.ndarray, raw: bytes, stats=None):
+    """apply one exported pass to `state` (complex64, length 2^n) in place"""
+    stats = stats if stats is not None else {}
+    head, segs, ops = parse(raw)
+    T = head.tile_bits
+    TB = T - K_REG
+    n_tiles = head.n_tiles
+    tile_pos = [head.tile.pos[i] for i in range(head.tile.n)]
+    assert head.tile.n == T and tile_pos[:5] == [0, 1, 2, 3, 4]
+    blk = np.arange(n_tiles, dtype=np.uint64)
+    gbase = deposit(blk, tile_pos)                                       # (tiles,)
+    tid = np.arange(1 << TB, dtype=np.uint32)
+    k = np.arange(32, dtype=np.uint32)
+
+    def global_index(toff, roff):
+        g_t = (tid & 31).astype(np.uint64) + _sum_cols(tid >> 5, [toff[j] for j in range(5, TB)], TB - 5)
+        g_r = _sum_cols(k, roff, K_REG)
+        return gbase[:, None, None] + g_t[None, :, None] + g_r[None, None, :]
+
+    gi = global_index(head.ld_toff, head.ld_roff)
+    assert len(np.unique(gi)) == gi.size == state.size, "entry layout does not cover the state exactly once"
+    a = state[gi]                                                        # (tiles, threads, 32)
+
+    for si, sg in enumerate(segs):
+        if sg.resplit:
+            assert si > 0
+            check_swizzle(sg, T, stats)
+            w = _xor_cols(tid, sg.wr_tcol, TB)[:, None] ^ _xor_cols(k, sg.wr_rcol, K_REG)[None, :]
+            r = _xor_cols(tid, sg.rd_tcol, TB)[:, None] ^ _xor_cols(k, sg.rd_rcol, K_REG)[None, :]
+            sm = np.empty((n_tiles, 1 << T), dtype=np.complex64)
+            sm[:, w.reshape(-1)] = a.reshape(n_tiles, -1)
+            a = sm[:, r.reshape(-1)].reshape(a.shape)
+            stats["resplits"] = stats.get("resplits", 0) + 1
+        else:
+            assert si == 0, "only the first segment may skip the re-split"
+        for op in ops[sg.first_op: sg.first_op + sg.n_ops]:
+            mux = bool(op.flags & TF_MUX)
+            blk_ok = (blk & np.uint64(op.b_mask)) == np.uint64(op.b_val)                 # (tiles,)
+            thr_ok = (tid & np.uint32(op.t_mask)) == np.uint32(op.t_val)                   # (threads,)
+            ok = blk_ok[:, None] & thr_ok[None, :]                                         # (tiles, threads)
+            ca, cb = list(op.a), list(op.b)
+            if op.kind == PHASE:
+                assert not mux
+                fac = np.complex64(complex(np.float32(ca[0]), np.float32(ca[1])))
+                sel = ((op.mask >> k) & 1).astype(bool)
+                m = ok[:, :, None] & sel[None, None, :]
+                a = np.where(m, (a * fac).astype(np.complex64), a)
+                continue
+            tk = op.tk
+            for p in range(16):
+                if not (op.mask >> p) & 1:
+                    continue
+                k0 = ((p >> tk) << (tk + 1)) | (p & ((1 << tk) - 1))
+                k1 = k0 | (1 << tk)
+                x, y = a[:, :, k0], a[:, :, k1]
+                xa, ya = butterfly(op.kind, x, y, ca)
+                if mux:
+                    xb, yb = butterfly(op.kind, x, y, cb)
+                    a[:, :, k0] = np.where(ok, xa, xb)
+                    a[:, :, k1] = np.where(ok, ya, yb)
+                else:
+                    a[:, :, k0] = np.where(ok, xa, x)
+                    a[:, :, k1] = np.where(ok, ya, y)
+
+    go = global_index(head.st_toff, head.st_roff)
+    assert len(np.unique(go)) == go.size == state.size, "exit layout does not cover the state exactly once"
+    if head.has_scale:
+        a = (a * np.complex64(complex(head.scale[0], head.scale[1]))).astype(np.complex64)
+    state[go] = a
+    return state
+
+
+def run_plan(plan, state: np.ndarray, stats=None):
+    info = plan.info()
+    assert info["n_fused_passes"] > 0, "plan has no fused passes"
+    state = np.array(state, dtype=np.complex64)
+    for i in range(info["n_fused_passes"]):
+        run_pass(state, plan.export_pass(i), stats)
+    return state
