@@ -56,6 +56,7 @@ struct FusedPass {
     uint64_t ld_toff[kMaxThreadBits], ld_roff[kRegBits], st_toff[kMaxThreadBits], st_roff[kRegBits];
     std::vector<TileSeg> segs;
     std::vector<TileOp> ops;
+    const DevOp* d_ops = nullptr;   // device copy (plan arena), ops.size() + 1 entries
 };
 
 }  // namespace aqs
@@ -65,8 +66,12 @@ struct aqs_plan_s {
     uint32_t flags = 0;
     std::vector<aqs::CanonOp> ops;       // per-gate path
     std::vector<aqs::FusedPass> passes;  // fused path (empty => run ops one by one)
+    void* arena = nullptr;               // device copy of every pass's DevOps
+    size_t arena_bytes = 0;
     cudaGraphExec_t graph = nullptr;     // AQS_PLAN_GRAPH: the launch sequence captured for `graph_state`
     const void* graph_state = nullptr;
+    cudaStream_t last_stream = nullptr;  // stream of the most recent run (synchronised before the arena is recycled)
+    bool ran = false;
     aqs_plan_info info{};
 };
 
@@ -97,9 +102,11 @@ static bool mat_equal(const cd* A, const cd* B) {
 // imaginary shear coefficients (tile_kernel.cuh, butterfly<>).  Falls back to TK_GEN (the direct
 // 8-instruction form) when the matrix has no such structure or the shears would be ill-conditioned.
 struct Decomp {
-    int kind = TK_GEN;
+    int kind = TK_GEN;       // TK_SHR, TK_SHI, TK_GEN, TK_PERM_R or TK_PERM_I
     float c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int cost = 8;            // FFMA2 per amplitude pair
+    double sx = 1.0, sy = 1.0;   // shears only: factors applied first to the target-bit-0 / target-bit-1 amplitudes
+    bool pre_imag = false;       // the prescale is (i*sx, i*sy)
+    int cost = 8;                // FFMA2 per amplitude pair, prescale included
 };
 
 // N (2x2 real, det 1, N00 >= 0 expected) = [[1+ab, a+g+abg],[b, 1+bg]]
@@ -174,23 +181,53 @@ static Decomp decompose(const cd* M) {
             if (err > 1e-9 || std::fabs(a) > 4.0 || std::fabs(g) > 4.0 || std::fabs(b) > 4.0) return gen();
         }
     }
-    const bool unit = sx == 1.0 && sy == 1.0;
-    d.c[0] = (float)a; d.c[1] = (float)b; d.c[2] = (float)g; d.c[3] = (float)sx; d.c[4] = (float)sy;
-    if (cls == 0) { d.kind = unit ? TK_SHR : TK_SHR_P; }
-    else if (cls == 1) { d.kind = unit ? TK_SHI : TK_SHI_P; }
-    else { d.kind = TK_SHI_Q; }
-    d.cost = (d.kind == TK_SHR || d.kind == TK_SHI) ? 3 : 5;
+    d.c[0] = (float)a; d.c[1] = (float)b; d.c[2] = (float)g;
+    d.kind = (cls == 0) ? TK_SHR : TK_SHI;
+    d.sx = sx; d.sy = sy;
+    d.pre_imag = (cls == 2);
+    // real factors ride inside the op (2 FMUL2 per pair); an imaginary prescale costs a separate op
+    d.cost = 3 + (d.pre_imag ? 4 : ((sx != 1.0 || sy != 1.0) ? 2 : 0));   // the prescale rides inside the op
     return d;
 }
 
-// cost model (FFMA2 per amplitude pair) used to decide merges
-static int mat_cost(const cd* M) {
+// Cost model used to decide merges, in FFMA2 per amplitude pair.  Every emitted tile op also pays
+// the interpreter's dispatch (~200 cycles per warp, i.e. about kDispatch FFMA2 per pair): what
+// counts is mostly HOW MANY ops a rewrite leaves.
+constexpr int kDispatch = 6;
+static int mat_cost(const cd* M) {        // one matrix applied alone, dispatch included
     if (mat_is_identity(M)) return 0;
-    if (mat_is_diag(M)) return z0(M[0] - 1.0) ? 1 : 2;
-    return decompose(M).cost;
+    if (mat_is_diag(M)) return kDispatch + (z0(M[0] - 1.0) ? 1 : 2);
+    const Decomp d = decompose(M);
+    return kDispatch + d.cost;
 }
-static int pop_cost2(const POp& o) {   // twice the average cost over the two branches
-    return o.mux < 0 ? 2 * mat_cost(o.m[0]) : mat_cost(o.m[0]) + mat_cost(o.m[1]);
+// twice the average cost over the two branches; a common factor of -1 / +-i is free (global phase)
+static int pair_cost(const cd* M0, const cd* M1, cd* best_f = nullptr) {
+    static const cd fs[4] = {cd(1, 0), cd(-1, 0), cd(0, 1), cd(0, -1)};
+    int best = 1 << 30;
+    for (const cd& f : fs) {
+        cd a[4], b[4];
+        for (int i = 0; i < 4; ++i) { a[i] = f * M0[i]; b[i] = f * M1[i]; }
+        int c;
+        if (mat_is_identity(a) && mat_is_identity(b)) c = 0;
+        else {
+            const Decomp da = decompose(a), db = decompose(b);
+            const bool ia = mat_is_identity(a), ib = mat_is_identity(b);
+            const bool shear_a = ia || da.kind <= TK_SHI, shear_b = ib || db.kind <= TK_SHI;
+            const bool same = shear_a && shear_b && (ia || ib || da.kind == db.kind);
+            if (same) {
+                // one multiplexed shear op
+                c = 2 * kDispatch + (ia ? 0 : da.cost) + (ib ? 0 : db.cost);
+            } else {
+                c = (ia ? 0 : 2 * kDispatch + da.cost) + (ib ? 0 : 2 * kDispatch + db.cost);
+            }
+        }
+        if (c < best) { best = c; if (best_f) *best_f = f; }
+    }
+    return best;
+}
+static int pop_cost2(const POp& o) {
+    if (o.diag) return 2 * mat_cost(o.m[0]);
+    return o.mux < 0 ? pair_cost(o.m[0], o.m[0]) : pair_cost(o.m[0], o.m[1]);
 }
 
 // bits on which the op acts NON-diagonally / diagonally
@@ -281,7 +318,7 @@ static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
                 }
                 mat_mul(u.m[0], prod.m[v], prod.m[v]);
                 // u alone would cost mat_cost(u) on one branch and nothing on the other
-                if (pop_cost2(prod) <= pop_cost2(w) + mat_cost(u.m[0])) {
+                if (pop_cost2(prod) <= pop_cost2(w) + mat_cost(u.m[0]) + kDispatch) {
                     // w now reads bit c: a non-diagonal op pending on c can no longer accept later merges
                     if (open[c] >= 0 && !out[open[c]].diag) open[c] = -1;
                     w = prod;
@@ -520,6 +557,11 @@ struct Emitter {
             }
         }
     }
+    void push(TileOp& t) const {
+        if (t.t_mask || t.b_mask) t.flags |= TF_PRED;
+        t.code = tile_op_code(t.kind, t.tk, t.mj, t.flags) | ((uint32_t)t.flags << 16);
+        out->push_back(t);
+    }
     static uint32_t pair_mask(int tk, uint32_t rk_mask, uint32_t rk_val) {
         uint32_t pairs = 0;
         for (int pr = 0; pr < kPairs; ++pr) {
@@ -528,65 +570,118 @@ struct Emitter {
         }
         return pairs;
     }
-    void emit_matrix(const cd* M, int tk, uint64_t cm, uint64_t cv) const {
-        if (mat_is_identity(M)) return;
+    // position of register bit r in the pair index of target register bit tk
+    static int pair_bit(int tk, int r) { return r < tk ? r : r - 1; }
+
+    // one factor on the amplitudes selected by (sm, sv); kind TK_PHASE / TK_SCALE_R / TK_SCALE_I
+    void emit_factor(int kind, double fr, double fi, uint64_t sm, uint64_t sv) const {
         TileOp t;
         std::memset(&t, 0, sizeof t);
-        const Decomp d = decompose(M);
-        t.kind = (uint8_t)d.kind;
-        t.tk = (uint8_t)tk;
-        for (int i = 0; i < 8; ++i) t.a[i] = d.c[i];
-        uint32_t rm, rv;
-        select(cm, cv, rm, rv, t);
-        t.mask = pair_mask(tk, rm, rv);
-        if (t.mask) out->push_back(t);
-    }
-    void emit_phase(cd f, uint64_t sm, uint64_t sv) const {
-        if (z0(f - 1.0)) return;
-        TileOp t;
-        std::memset(&t, 0, sizeof t);
-        t.kind = TK_PHASE;
-        t.a[0] = (float)f.real();
-        t.a[1] = (float)f.imag();
+        t.kind = (uint8_t)kind;
+        t.a[0] = (float)fr;
+        t.a[1] = (float)fi;
         uint32_t rm, rv;
         select(sm, sv, rm, rv, t);
         uint32_t act = 0;
         for (uint32_t k = 0; k < (uint32_t)kRegs; ++k)
             if ((k & rm) == rv) act |= 1u << k;
+        if (!act) return;
         t.mask = act;
-        if (act) out->push_back(t);
+        if (rm == 0) t.mj = 5;
+        else if (popc(rm) == 1) t.mj = (uint8_t)(__builtin_ctz(rm) + (rv ? 0 : 8));
+        else t.mj = 6;
+        push(t);
     }
-    // Bring two decompositions to one kind (for a per-thread coefficient select); false if impossible cheaply.
-    static bool common_kind(const cd* M0, const cd* M1, Decomp& d0, Decomp& d1) {
-        d0 = decompose(M0);
-        d1 = decompose(M1);
-        auto promote = [](Decomp& d, int kind) {
-            if (d.kind == kind) return true;
-            if ((d.kind == TK_SHR && kind == TK_SHR_P) || (d.kind == TK_SHI && kind == TK_SHI_P)) {
-                d.kind = kind; d.c[3] = 1.f; d.c[4] = 1.f; d.cost = 5;
-                return true;
-            }
-            return false;
-        };
-        auto is_id = [](const cd* M) { return mat_is_identity(M); };
-        // the identity fits every shear family: all coefficients zero
-        auto as_identity = [](Decomp& d, int kind) {
-            d = Decomp();
-            d.kind = kind;
-            d.c[3] = d.c[4] = 1.f;
-            d.cost = (kind == TK_SHR || kind == TK_SHI) ? 3 : 5;
-        };
-        if (is_id(M0) && d1.kind <= TK_SHI_P) { as_identity(d0, d1.kind); return true; }
-        if (is_id(M1) && d0.kind <= TK_SHI_P) { as_identity(d1, d0.kind); return true; }
-        if (d0.kind == d1.kind && d0.kind != TK_GEN) return true;
-        if (d0.kind > TK_SHI_Q || d1.kind > TK_SHI_Q) return false;
-        const int fam0 = (d0.kind == TK_SHR || d0.kind == TK_SHR_P) ? 0 : (d0.kind == TK_SHI || d0.kind == TK_SHI_P) ? 1 : 2;
-        const int fam1 = (d1.kind == TK_SHR || d1.kind == TK_SHR_P) ? 0 : (d1.kind == TK_SHI || d1.kind == TK_SHI_P) ? 1 : 2;
-        if (fam0 == fam1 && fam0 < 2) {
-            const int k = fam0 == 0 ? TK_SHR_P : TK_SHI_P;
-            return promote(d0, k) && promote(d1, k);
+    void emit_phase(cd f, uint64_t sm, uint64_t sv) const {
+        if (z0(f - 1.0)) return;
+        if (z0(f.imag())) { emit_factor(TK_SCALE_R, f.real(), 0.0, sm, sv); return; }
+        if (z0(f.real())) { emit_factor(TK_SCALE_I, f.imag(), 0.0, sm, sv); return; }
+        // f = rho * e^{i theta}: the kernel rotates (re, im) by |theta| <= pi/2 with three shears; a
+        // sign or a modulus other than 1 goes first as a real scale
+        double rho = std::abs(f), theta = std::arg(f);
+        bool neg = false;
+        if (theta > M_PI / 2) { theta -= M_PI; neg = true; }
+        else if (theta < -M_PI / 2) { theta += M_PI; neg = true; }
+        if (std::fabs(rho - 1.0) > 3e-7) emit_factor(TK_SCALE_R, rho, 0.0, sm, sv);
+        emit_factor(neg ? TK_PHASE_N : TK_PHASE, -std::tan(0.5 * theta), std::sin(theta), sm, sv);
+    }
+    // The prescale of a shear decomposition rides inside the shear op (TF_PY): real factors for both
+    // families, purely imaginary ones (the X * RotX family) for TK_SHI.
+    // butterfly of one decomposition under controls (cm, cv); d0 != nullptr: multiplexed on `mux_bit`
+    // (d applies where the bit is 1, *d0 where it is 0) — both must be the same shear kind
+    void emit_butterfly(const Decomp& d, const Decomp* d0, int mux_bit, int tk, uint64_t cm, uint64_t cv) const {
+        TileOp t;
+        std::memset(&t, 0, sizeof t);
+        t.kind = (uint8_t)d.kind;
+        t.tk = (uint8_t)tk;
+        for (int i = 0; i < 8; ++i) t.a[i] = d.c[i];
+        uint32_t rm, rv;
+        select(cm, cv, rm, rv, t);
+        const bool shearing = d.kind <= TK_SHI;
+        if (shearing) {
+            // c[3] = factor on y; the op needs the prescale variant when any set has one
+            t.a[3] = (float)d.sy;
+            t.b[3] = d0 ? (float)d0->sy : 1.f;
+            t.sx[0] = (float)d.sx;
+            t.sx[1] = d0 ? (float)d0->sx : 1.f;
+            if (d.sy != 1.0 || d.sx != 1.0 || d.pre_imag || (d0 && (d0->sy != 1.0 || d0->sx != 1.0 || d0->pre_imag))) t.flags |= TF_PY;
+            if (d.pre_imag) t.flags |= TF_IMAG_A;
+            if (d0 && d0->pre_imag) t.flags |= TF_IMAG_B;
         }
-        return false;
+        if (d0) {
+            // the multiplexing bit: register -> pair subsets; thread / outside the tile -> predicate picks the set
+            for (int i = 0; i < 3; ++i) t.b[i] = d0->c[i];
+            const int mj = local_of_bit[mux_bit];
+            if (mj >= 0 && L->reg_of[mj] >= 0) {
+                t.flags |= TF_REGMUX;
+                t.mj = (uint8_t)pair_bit(tk, L->reg_of[mj]);
+                t.mask = pair_mask(tk, 1u << L->reg_of[mj], 1u << L->reg_of[mj]);
+            } else {
+                t.flags |= TF_MUX;
+                t.mask = 0xffffu;
+                TileOp sel;
+                std::memset(&sel, 0, sizeof sel);
+                uint32_t a2, b2;
+                select(1ull << mux_bit, 1ull << mux_bit, a2, b2, sel);
+                t.t_mask = sel.t_mask; t.t_val = sel.t_val; t.b_mask = sel.b_mask; t.b_val = sel.b_val;
+            }
+            push(t);
+            return;
+        }
+        t.mask = pair_mask(tk, rm, rv);
+        if (!t.mask) return;
+        if (shearing) {
+            if (rm == 0) {
+                t.mj = 0;                       // every pair: the kernel uses set a for both subsets
+            } else if (popc(rm) == 1 && rv == rm) {
+                t.flags |= TF_REGMUX;           // one control on a register bit: set b = identity leaves the other pairs alone
+                t.mj = (uint8_t)pair_bit(tk, __builtin_ctz(rm));
+                for (int i = 0; i < 8; ++i) t.b[i] = 0.f;
+                t.b[3] = 1.f;
+            } else if (popc(rm) == 1) {
+                // control value 0: swap the roles (identity on the pairs with the bit set)
+                t.flags |= TF_REGMUX;
+                t.mj = (uint8_t)pair_bit(tk, __builtin_ctz(rm));
+                for (int i = 0; i < 8; ++i) { t.b[i] = t.a[i]; t.a[i] = 0.f; }
+                t.a[3] = 1.f;
+                t.sx[1] = t.sx[0];
+                t.sx[0] = 1.f;
+                if (t.flags & TF_IMAG_A) t.flags = (uint8_t)((t.flags & ~TF_IMAG_A) | TF_IMAG_B);
+                t.mask = pair_mask(tk, rm, rm);
+            } else {
+                t.flags |= TF_REGMUX;
+                t.mj = 4;                       // generic mask
+                for (int i = 0; i < 8; ++i) t.b[i] = 0.f;
+                t.b[3] = 1.f;
+            }
+        }
+        push(t);
+    }
+    void emit_matrix(const cd* M, int bit, int tk, uint64_t cm, uint64_t cv) const {
+        if (mat_is_identity(M)) return;
+        const Decomp d = decompose(M);
+        (void)bit;
+        emit_butterfly(d, nullptr, -1, tk, cm, cv);
     }
     void emit(const POp& o, cd& pass_scale) const {
         const uint64_t tb = 1ull << o.p;
@@ -605,49 +700,33 @@ struct Emitter {
             return;
         }
         const int tk = L->reg_of[local_of_bit[o.p]];
-        if (o.mux < 0) {
-            if (o.cmask == 0) {
-                // a common factor of the prescale (-1, or +-i for the AXLIKE family) is a global
-                // phase: it goes to the pass-wide scale and the op loses its prescale
-                const Decomp d = decompose(o.m[0]);
-                if ((d.kind == TK_SHR_P || d.kind == TK_SHI_P || d.kind == TK_SHI_Q) && d.c[3] == d.c[4]) {
-                    pass_scale *= (d.kind == TK_SHI_Q) ? cd(0.0, d.c[3]) : cd(d.c[3], 0.0);
-                    TileOp t;
-                    std::memset(&t, 0, sizeof t);
-                    t.kind = (uint8_t)(d.kind == TK_SHR_P ? TK_SHR : TK_SHI);
-                    t.tk = (uint8_t)tk;
-                    t.mask = 0xffffu;
-                    for (int i = 0; i < 3; ++i) t.a[i] = d.c[i];
-                    out->push_back(t);
-                    return;
-                }
+        cd m0[4], m1[4];
+        for (int i = 0; i < 4; ++i) { m0[i] = o.m[0][i]; m1[i] = o.m[o.mux < 0 ? 0 : 1][i]; }
+        if (o.cmask == 0) {
+            // a common factor -1 / +-i that makes the decompositions cheaper is a global phase
+            cd f(1, 0);
+            pair_cost(m0, m1, &f);
+            if (f != cd(1, 0)) {
+                for (int i = 0; i < 4; ++i) { m0[i] *= f; m1[i] *= f; }
+                pass_scale *= std::conj(f);
             }
-            emit_matrix(o.m[0], tk, o.cmask, o.cval);
+        }
+        if (o.mux < 0) {
+            emit_matrix(m0, o.p, tk, o.cmask, o.cval);
             return;
         }
         const uint64_t mb = 1ull << o.mux;
-        const int mj = local_of_bit[o.mux];
-        const bool lane_mux = mj >= 0 && L->thr_of[mj] >= 0 && L->thr_of[mj] < kLaneBits;
-        if (lane_mux && o.cmask == 0) {
-            // the control is a lane bit: one op, each thread picks its coefficient set
-            Decomp d0, d1;
-            if (common_kind(o.m[0], o.m[1], d0, d1) && d0.cost <= mat_cost(o.m[0]) + mat_cost(o.m[1])) {
-                TileOp t;
-                std::memset(&t, 0, sizeof t);
-                t.kind = (uint8_t)d1.kind;
-                t.tk = (uint8_t)tk;
-                t.flags = TF_MUX;
-                t.mask = 0xffffu;
-                t.t_mask = (uint16_t)(1u << L->thr_of[mj]);
-                t.t_val = t.t_mask;
-                for (int i = 0; i < 8; ++i) { t.a[i] = d1.c[i]; t.b[i] = d0.c[i]; }
-                out->push_back(t);
-                return;
-            }
+        Decomp d0 = decompose(m0), d1 = decompose(m1);
+        // the identity is a shear of either family with zero coefficients
+        if (mat_is_identity(m0) && d1.kind <= TK_SHI) { d0 = Decomp(); d0.kind = d1.kind; d0.cost = 0; }
+        if (mat_is_identity(m1) && d0.kind <= TK_SHI) { d1 = Decomp(); d1.kind = d0.kind; d1.cost = 0; }
+        // (a default Decomp has zero shear coefficients and sx = sy = 1: the identity)
+        if (o.cmask == 0 && d0.kind == d1.kind && d0.kind <= TK_SHI) {
+            emit_butterfly(d1, &d0, o.mux, tk, 0, 0);
+            return;
         }
-        // control on a register bit (pair subsets), a warp bit or a bit outside the tile (uniform predicates)
-        emit_matrix(o.m[0], tk, o.cmask | mb, o.cval);
-        emit_matrix(o.m[1], tk, o.cmask | mb, o.cval | mb);
+        emit_matrix(m0, o.p, tk, o.cmask | mb, o.cval);
+        emit_matrix(m1, o.p, tk, o.cmask | mb, o.cval | mb);
     }
 };
 
@@ -664,6 +743,14 @@ static int build_fused(aqs_plan_s* p) {
     const size_t kMaxTake = kOpsLarge / 2;     // every planner op emits at most two tile ops
 
     std::vector<POp> ops = simplify(n, p->ops);
+    if (std::getenv("AQS_PLAN_DUMP") && std::atoi(std::getenv("AQS_PLAN_DUMP")) > 2)
+        for (size_t i = 0; i < ops.size(); ++i) {
+            const POp& o = ops[i];
+            std::fprintf(stderr, "  op %zu: bit %d %s cmask %llx mux %d cost %d/%d  m0 = [%.3f%+.3fi %.3f%+.3fi; %.3f%+.3fi %.3f%+.3fi]\n", i, o.p,
+                         o.diag ? "diag" : "mat", (unsigned long long)o.cmask, o.mux, mat_cost(o.m[0]), o.mux >= 0 ? mat_cost(o.m[1]) : -1,
+                         o.m[0][0].real(), o.m[0][0].imag(), o.m[0][1].real(), o.m[0][1].imag(), o.m[0][2].real(), o.m[0][2].imag(),
+                         o.m[0][3].real(), o.m[0][3].imag());
+        }
     // Sliding window over the op stream: a pass looks at the ops deferred by earlier passes plus
     // the next kWindow ops, so planning is O(passes * window) even for million-op circuits
     // (Grover-26 with 6433 iterations lowers to ~1e6 ops).
@@ -802,9 +889,43 @@ static int build_fused(aqs_plan_s* p) {
     return AQS_OK;
 }
 
-template <int CAP>
-static void fill_params(PassParams<CAP>& P, float2* state, const FusedPass& fp) {
+// Device copy of every pass's op descriptors, made on first use so that plans can be built (and
+// inspected) without a GPU.
+static int ensure_uploaded(aqs_plan_s* p) {
+    if (p->arena || p->passes.empty()) return AQS_OK;
+    size_t total = 0;
+    for (auto& fp : p->passes) total += fp.ops.size() + 1;
+    std::vector<DevOp> host(total);
+    std::memset(host.data(), 0, total * sizeof(DevOp));
+    cudaError_t e = pool_alloc(&p->arena, total * sizeof(DevOp));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(plan arena)", __LINE__);
+    p->arena_bytes = total * sizeof(DevOp);
+    size_t off = 0;
+    for (auto& fp : p->passes) {
+        fp.d_ops = reinterpret_cast<const DevOp*>(p->arena) + off;
+        for (const TileOp& t : fp.ops) {
+            DevOp& d = host[off++];
+            d.word = t.code;
+            d.sx_a = t.sx[0];
+            d.sx_b = t.sx[1];
+            d.mask = t.mask;
+            d.tpred = (uint32_t)t.t_mask | ((uint32_t)t.t_val << 16);
+            d.b_mask = t.b_mask;
+            d.b_val = t.b_val;
+            for (int i = 0; i < 4; ++i) { d.a[i] = t.a[i]; d.b[i] = (t.kind == TK_GEN) ? t.a[4 + i] : t.b[i]; }
+        }
+        host[off++].word = kDevOpEnd << 3;   // sentinel: read by the prefetch, never executed
+    }
+    e = cudaMemcpy(p->arena, host.data(), total * sizeof(DevOp), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(plan arena)", __LINE__);
+    count_h2d(total * sizeof(DevOp));
+    return AQS_OK;
+}
+
+static void fill_params(PassParams& P, float2* state, const FusedPass& fp) {
+    std::memset(&P, 0, sizeof P);
     P.state = state;
+    P.ops = fp.d_ops;
     P.n_segs = (uint32_t)fp.segs.size();
     P.n_ops = (uint32_t)fp.ops.size();
     P.scale = fp.scale;
@@ -816,44 +937,38 @@ static void fill_params(PassParams<CAP>& P, float2* state, const FusedPass& fp) 
     std::memcpy(P.st_roff, fp.st_roff, sizeof P.st_roff);
     P.tile = fp.tile;
     std::memcpy(P.segs, fp.segs.data(), fp.segs.size() * sizeof(TileSeg));
-    std::memcpy(P.ops, fp.ops.data(), fp.ops.size() * sizeof(TileOp));
 }
 
-template <int T, int CAP>
-static cudaError_t launch_tile(float2* state, const FusedPass& fp, cudaStream_t st) {
-    static PassParams<CAP> P;            // zero-initialised once; only the used prefix is rewritten
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    fill_params(P, state, fp);
-    constexpr size_t smem = sizeof(float2) << T;
-    k_tile2<T, CAP><<<(unsigned)fp.n_tiles, 1 << (T - kRegBits), smem, st>>>(P);
+static size_t tile_smem_bytes(int T, size_t n_ops) { return (sizeof(float2) << T) + (n_ops + 1) * sizeof(DevOp); }
+
+template <int T>
+static cudaError_t launch_tile(const PassParams& P, const FusedPass& fp, cudaStream_t st) {
+    k_tile2<T><<<(unsigned)fp.n_tiles, 1 << (T - kRegBits), tile_smem_bytes(T, fp.ops.size()), st>>>(P);
     return cudaGetLastError();
-}
-
-template <int CAP>
-static cudaError_t launch_tile_t(float2* state, const FusedPass& fp, cudaStream_t st) {
-    switch (fp.T) {
-        case 10: return launch_tile<10, CAP>(state, fp, st);
-        case 11: return launch_tile<11, CAP>(state, fp, st);
-        case 12: return launch_tile<12, CAP>(state, fp, st);
-        default: return launch_tile<13, CAP>(state, fp, st);
-    }
 }
 
 static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st) {
     if (fp.n_tiles > 0x7fffffffull) return fail(AQS_ERR_INVALID, "grid too large");
-    const cudaError_t e = (fp.ops.size() <= (size_t)kOpsSmall) ? launch_tile_t<kOpsSmall>(state, fp, st)
-                                                               : launch_tile_t<kOpsLarge>(state, fp, st);
+    PassParams P;
+    fill_params(P, state, fp);
+    cudaError_t e;
+    switch (fp.T) {
+        case 10: e = launch_tile<10>(P, fp, st); break;
+        case 11: e = launch_tile<11>(P, fp, st); break;
+        case 12: e = launch_tile<12>(P, fp, st); break;
+        default: e = launch_tile<13>(P, fp, st); break;
+    }
     if (e != cudaSuccess) return fail_cuda(e, "tile kernel launch", __LINE__);
     count_launch(1);
     return AQS_OK;
 }
 
 int fused_init() {
-    // 64 KiB of dynamic shared memory for the 13-bit tile needs the opt-in
-    cudaError_t e = cudaFuncSetAttribute(k_tile2<13, kOpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) << 13));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_tile2<13, kOpsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) << 13));
+    // tile + descriptors exceed the 48 KiB default of dynamic shared memory: opt in once
+    cudaError_t e = cudaFuncSetAttribute(k_tile2<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(10, kOpsLarge));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(11, kOpsLarge));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(12, kOpsLarge));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(13, kOpsLarge));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tile kernel)", __LINE__);
     return AQS_OK;
 }
@@ -902,17 +1017,18 @@ int aqs_plan_build(int n, const aqs_op* ops, uint64_t n_ops, uint32_t flags, aqs
             if (std::atoi(std::getenv("AQS_PLAN_DUMP")) > 1)
                 for (size_t i = 0; i < p->passes.size(); ++i) {
                     auto& fp = p->passes[i];
-                    int km[16] = {0}, masked = 0, muxed = 0, cost = 0;
+                    int km[16] = {0}, generic = 0, muxed = 0, cost = 0;
                     for (auto& t : fp.ops) {
                         km[t.kind & 15]++;
-                        const bool full = (t.kind == TK_PHASE) ? (t.mask == 0xffffffffu) : (t.mask == 0xffffu);
-                        masked += !full;
-                        muxed += (t.flags & TF_MUX) != 0;
-                        const int per = (t.kind == TK_SHR || t.kind == TK_SHI) ? 3 : (t.kind == TK_GEN ? 8 : ((t.kind == TK_PHASE || t.kind >= TK_PERM_R) ? 2 : 5));
-                        cost += per * popc(t.mask);
+                        const bool factor = t.kind >= TK_PHASE;
+                        generic += factor ? (t.mj == 6) : (t.kind <= TK_SHI ? (t.mj == 4) : (t.mask != 0xffffu));
+                        muxed += (t.flags & (TF_MUX | TF_REGMUX)) != 0;
+                        cost += factor ? (t.kind == TK_PHASE ? 2 : 1) * popc(t.mask)
+                                       : (t.kind <= TK_SHI ? 3 * kPairs : (t.kind == TK_GEN ? 8 : 2) * popc(t.mask));
                     }
-                    std::fprintf(stderr, "  pass %zu: %zu ops in %zu layouts [shr %d shr_p %d shi %d shi_p %d shi_q %d gen %d phase %d perm %d | masked %d mux %d | ~%d ffma2/thread], tile bits",
-                                 i, fp.ops.size(), fp.segs.size(), km[0], km[1], km[2], km[3], km[4], km[5], km[6], km[7] + km[8], masked, muxed, cost);
+                    std::fprintf(stderr, "  pass %zu: %zu ops in %zu layouts [shr %d shi %d gen %d perm %d phase %d scale %d | generic-mask %d mux %d | ~%d ffma2/thread], tile bits",
+                                 i, fp.ops.size(), fp.segs.size(), km[TK_SHR], km[TK_SHI], km[TK_GEN], km[TK_PERM_R] + km[TK_PERM_I],
+                                 km[TK_PHASE] + km[TK_PHASE_N], km[TK_SCALE_R] + km[TK_SCALE_I], generic, muxed, cost);
                     for (int j = 0; j < fp.tile.n; ++j) std::fprintf(stderr, " %d", fp.tile.pos[j]);
                     std::fprintf(stderr, "\n");
                 }
@@ -948,6 +1064,10 @@ static int launch_all(aqs_state_t s, aqs_plan_t p) {
 int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
     if (!s || !p) return fail(AQS_ERR_INVALID, "null handle");
     if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
+    int up = ensure_uploaded(p);
+    if (up) return up;
+    p->last_stream = s->stream;
+    p->ran = true;
     if (p->flags & AQS_PLAN_GRAPH) {
         // launch-bound plans (small states, thousands of passes): replay one CUDA graph instead of
         // issuing every launch from the host.  The graph bakes in the state's buffer, so it is
@@ -1018,7 +1138,9 @@ int aqs_plan_export_pass(aqs_plan_t p, uint64_t index, void* buf, uint64_t cap, 
 
 int aqs_plan_destroy(aqs_plan_t p) {
     if (!p) return AQS_OK;
+    if (p->ran && p->arena && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();   // kernels may still read the arena
     if (p->graph) cudaGraphExecDestroy(p->graph);
+    if (p->arena) pool_free(p->arena, p->arena_bytes);
     delete p;
     return AQS_OK;
 }

@@ -47,39 +47,59 @@ constexpr int kMinTileBits = kLaneBits + kRegBits;   // 10
 constexpr int kMaxTileBits = 13;                     // 8192 amplitudes = 64 KiB of shared memory
 constexpr int kMaxThreadBits = kMaxTileBits - kRegBits;
 constexpr int kMaxSegs = 24;
-constexpr int kOpsSmall = 36;
-constexpr int kOpsLarge = 300;
+constexpr int kOpsLarge = 300;            // ops per pass (shared memory: 64 bytes each)
 
 enum TileKind : uint8_t {
-    TK_SHR = 0,      // real shears:                      c = {a, b, g}
-    TK_SHR_P = 1,    // real prescale then real shears:   c = {a, b, g, sx, sy}
-    TK_SHI = 2,      // imaginary shears i*a, i*b, i*g:   c = {a, b, g}
-    TK_SHI_P = 3,    // real prescale, imaginary shears:  c = {a, b, g, sx, sy}
-    TK_SHI_Q = 4,    // imaginary prescale i*sx, i*sy, imaginary shears
-    TK_GEN = 5,      // general complex 2x2, direct:      c = {m00.re, m00.im, m01.re, ... m11.im}
-    TK_PHASE = 6,    // one complex factor on selected registers: c = {re, im}
-    TK_PERM_R = 7,   // anti-diagonal, real entries:  x' = c0*y, y' = c1*x  (X, CX, Swap: exact data movement)
-    TK_PERM_I = 8    // anti-diagonal, imaginary:     x' = i*c0*y, y' = i*c1*x  (Y)
+    // butterflies on register pairs (mask = 16-bit pair mask)
+    TK_SHR = 0,      // real shears       x += a*y; y += b*x; x += g*y           c = {a, b, g}
+    TK_SHI = 1,      // imaginary shears  x += i*a*y; y += i*b*x; x += i*g*y     c = {a, b, g}
+    TK_GEN = 2,      // general complex 2x2, direct: c = {m00.re, m00.im, m01.re, ... m11.im}
+    TK_PERM_R = 3,   // anti-diagonal, real entries:  x' = c0*y, y' = c1*x  (X, CX, Swap: exact data movement)
+    TK_PERM_I = 4,   // anti-diagonal, imaginary:     x' = i*c0*y, y' = i*c1*x  (Y)
+    // factors on single registers (mask = 32-bit register mask)
+    TK_PHASE = 5,    // unit-modulus factor e^{i theta}, |theta| <= pi/2:  c = {-tan(theta/2), sin(theta)}
+    TK_SCALE_R = 6,  // real factor     c = {s}
+    TK_SCALE_I = 7,  // imaginary factor i*s
+    TK_PHASE_N = 8   // -e^{i theta}: the same three shears with negated accumulators (pi/2 < |angle| <= pi)
 };
 enum TileFlags : uint8_t {
-    TF_MUX = 1       // threads/CTAs whose predicate is false use coefficient set b instead of skipping
+    TF_MUX = 1,      // threads/CTAs whose predicate is false use coefficient set b instead of skipping
+    TF_REGMUX = 2,   // TK_SHR / TK_SHI: pairs in `mask` use set a, all other pairs use set b
+    TF_PRED = 4,     // t_mask or b_mask is non-zero (set by the planner; lets plain ops skip the predicate code)
+    TF_PY = 8,       // shears: each set carries factors (sx, sy) applied first to x and y: reflections (CX
+                     // folded into a rotation) and sign fixes ride inside the op.  sy = c[3]; sx = TileOp.sx[set]
+    TF_IMAG_A = 16,  // TK_SHI with TF_PY: set a's factors are i*sx, i*sy (the X * RotX family)
+    TF_IMAG_B = 32   // same for set b
 };
 
 struct alignas(16) TileOp {
     uint8_t kind;
     uint8_t tk;          // register bit of the target (butterfly kinds)
     uint8_t flags;
-    uint8_t pad0;
-    uint32_t mask;       // butterfly kinds: bit p = register pair p takes part (16 bits); PHASE: bit k = register k
+    uint8_t mj;          // how `mask` is structured, so that the kernel resolves it at compile time:
+                         //   shears: 0..3 = pairs whose pair-index bit mj is set (set a; the others set b), 4 = generic
+                         //   factors: 0..4 = registers whose bit mj is set, 8..12 = whose bit mj-8 is clear, 5 = all registers, 6 = generic
+    uint32_t mask;       // butterfly kinds: bit p = register pair p takes part (16 bits); factor kinds: bit k = register k
     uint16_t t_mask;     // predicate on threadIdx.x: (tid & t_mask) == t_val
     uint16_t t_val;
+    uint32_t code;       // tile_op_code(kind, tk, mj) | flags << 16: the one word the interpreter loop reads
     uint32_t b_mask;     // predicate on blockIdx.x (control bits outside the tile, in compact tile-number space)
     uint32_t b_val;
-    uint32_t pad1[3];
+    float sx[2];         // TF_PY: factor on x for set a / set b
     float a[8];          // coefficient set used where the predicate holds
     float b[8];          // TF_MUX: coefficient set used where it does not
 };
 static_assert(sizeof(TileOp) == 96, "TileOp layout");
+
+// dispatch code = group * 8 + sub:
+//   shears:  group = kind * 5 + tk (+ 10 with TF_PY)  (0..19),  sub = mj (0..4)
+//   direct:  group = 20 + kind - TK_GEN (20..22),                sub = tk
+//   factors: group = 23 + (kind - TK_PHASE) * 2 + hi (23..30),   sub = pattern & 7, pattern = mj (0..6) or mj - 1 (7..11), hi = pattern >> 3
+__host__ __device__ constexpr uint32_t tile_op_code(uint32_t kind, uint32_t tk, uint32_t mj, uint32_t flags) {
+    return kind <= 1 ? ((kind * 5u + tk + ((flags & 8u) ? 10u : 0u)) << 3) | mj
+         : kind <= 4 ? ((20u + kind - 2u) << 3) | tk
+                     : ((23u + (kind - 5u) * 2u + ((mj >= 8u ? mj - 1u : mj) >> 3)) << 3) | ((mj >= 8u ? mj - 1u : mj) & 7u);
+}
 
 // One layout plus the ops executed in it.  Slot index (in float2 units) of the amplitude held by
 // thread `tid` in register k:   XOR_j (tid bit j ? tcol[j] : 0)  ^  XOR_i (k bit i ? rcol[i] : 0).
@@ -95,9 +115,28 @@ struct alignas(16) TileSeg {
 };
 static_assert(sizeof(TileSeg) == 64, "TileSeg layout");
 
-template <int CAP>
+// What the kernel reads per op: the 64-byte compaction of a TileOp.  A pass's DevOps live in global
+// memory (plan arena); every CTA copies them into shared memory once, because the interpreter's
+// dependent loads must be cheap: an indexed LDC from the kernel-parameter bank costs >100 cycles,
+// four of them per op in a chain made the whole kernel latency-bound.
+struct alignas(16) DevOp {
+    uint32_t word;       // tile_op_code(kind, tk, mj) | flags << 16
+    uint32_t mask;
+    uint32_t tpred;      // t_mask | t_val << 16
+    float sx_a;          // TF_PY: factor on x, set a
+    uint32_t b_mask;
+    uint32_t b_val;
+    float sx_b;          // TF_PY: factor on x, set b
+    uint32_t pad1;
+    float a[4];          // TK_GEN: c[0..3]
+    float b[4];          // TK_GEN: c[4..7]
+};
+static_assert(sizeof(DevOp) == 64, "DevOp layout");
+constexpr uint32_t kDevOpEnd = 0xffu;   // group value of the sentinel that follows the last op
+
 struct alignas(16) PassParams {
     float2* state;
+    const DevOp* ops;      // n_ops + 1 entries (sentinel), global memory
     uint32_t n_segs;
     uint32_t n_ops;
     float2 scale;          // global factor of the pass (phases folded out of RotZ-like ops)
@@ -111,9 +150,8 @@ struct alignas(16) PassParams {
     uint64_t st_roff[kRegBits];
     BitList tile;          // global positions of the tile bits, ascending (tile.pos[0..4] = 0..4)
     TileSeg segs[kMaxSegs];
-    TileOp ops[CAP];
 };
-static_assert(sizeof(PassParams<kOpsLarge>) <= 32764, "kernel parameter space");
+static_assert(sizeof(PassParams) <= 4096, "kernel parameter space");
 
 // ---- packed f32x2 helpers ---------------------------------------------------
 struct f2 { unsigned long long v; };
@@ -153,40 +191,77 @@ __device__ __forceinline__ f2 fma_i(float s, f2 v, f2 acc) { return fma2(pk(-s, 
 // ptxas has nothing to rename across the interpreter's switch (a direct "x' = m00 x + m01 y"
 // needs both old values for both outputs; ptxas then parks results in fresh registers and copies
 // 32 pairs back at every join).  A rotation by |phi| <= pi/2 is a = g = -tan(phi/2), b = sin(phi)
-// (all <= 1 in magnitude); reflections and sign fixes go into (sx, sy).  The same identity holds
-// with imaginary shear coefficients for the RotX family.  3 FFMA2 per pair instead of 4.
+// (all <= 1 in magnitude); reflections and sign fixes are separate TK_SCALE_* ops.  The same
+// identity holds with imaginary shear coefficients for the RotX family.  3 FFMA2 per pair.
+//
+// Pair subsets are resolved at COMPILE time: an op carries two coefficient sets and the index J of
+// a pair-index bit; pairs with that bit set use set a, the others set b (J is where a control that
+// sits on a register bit lands in the pair index).  A plain op passes a == b, a controlled op
+// passes b = 0 (x += 0*y leaves x untouched), a multiplexed op (CX folded into a rotation) both.
+// Predicated FFMA2 is not an option: ptxas turns "@p FFMA2" into FFMA2 + 2 SEL.
+struct ShearCoef {
+    float a, b, g, sy, sx;
+    float qy, qx;      // TK_SHI with a prescale: the factors are (sx + i qx), (sy + i qy)
+};
+
+template <int KIND, bool PY>
+__device__ __forceinline__ void shear(f2& x, f2& y, const ShearCoef& k) {
+    if (KIND == TK_SHR) {
+        if (PY) {
+            x = mul2(bc(k.sx), x);
+            y = mul2(bc(k.sy), y);
+        }
+        asm("{\n\t.reg .b64 ka, kb, kg;\n\t"
+            "mov.b64 ka, {%2, %2};\n\tmov.b64 kb, {%3, %3};\n\tmov.b64 kg, {%4, %4};\n\t"
+            "fma.rn.f32x2 %0, ka, %1, %0;\n\tfma.rn.f32x2 %1, kb, %0, %1;\n\tfma.rn.f32x2 %0, kg, %1, %0;\n\t}"
+            : "+l"(x.v), "+l"(y.v) : "f"(k.a), "f"(k.b), "f"(k.g));
+    } else {
+        // x += i*a*y etc. on the halves with scalar FFMA (same FMA-pipe time as three FFMA2; the packed
+        // form needs (-c, c) operand pairs that ptxas keeps rebuilding with MOVs)
+        float xr = lo(x), xi = hi(x), yr = lo(y), yi = hi(y);
+        if (PY) {
+            // complex factors (real or purely imaginary in practice; the set decides at run time)
+            const float tx = xr * k.sx - xi * k.qx;
+            xi = fmaf(xr, k.qx, xi * k.sx);
+            xr = tx;
+            const float ty = yr * k.sy - yi * k.qy;
+            yi = fmaf(yr, k.qy, yi * k.sy);
+            yr = ty;
+        }
+        xr = fmaf(-k.a, yi, xr); xi = fmaf(k.a, yr, xi);
+        yr = fmaf(-k.b, xi, yr); yi = fmaf(k.b, xr, yi);
+        xr = fmaf(-k.g, yi, xr); xi = fmaf(k.g, yr, xi);
+        x = pk(xr, xi);
+        y = pk(yr, yi);
+    }
+}
+
+// Per-op prelude shared by every body: evaluates the predicate only when the planner flagged one.
+// Returns false when this thread skips the op; `use_b` = take coefficient set b (TF_MUX).
+__device__ __forceinline__ bool op_predicate(const DevOp& op, uint32_t flags, uint32_t tpred, uint32_t tid, bool& use_b) {
+    use_b = false;
+    if (flags & TF_PRED) {
+        const uint2 blk = *reinterpret_cast<const uint2*>(&op.b_mask);
+        const bool ok = ((blockIdx.x & blk.x) == blk.y) && ((tid & (tpred & 0xffffu)) == (tpred >> 16));
+        if (!ok) {
+            if (!(flags & TF_MUX)) return false;
+            use_b = true;
+        }
+    }
+    return true;
+}
+
+// the rare kinds: direct general 2x2 and the exact anti-diagonal moves
 template <int KIND>
-__device__ __forceinline__ void butterfly(f2& x, f2& y, const float (&c)[8]) {
-    if (KIND == TK_SHR || KIND == TK_SHR_P) {
-        if (KIND == TK_SHR_P) {
-            x = mul2(bc(c[3]), x);
-            y = mul2(bc(c[4]), y);
-        }
-        x = fma2(bc(c[0]), y, x);
-        y = fma2(bc(c[1]), x, y);
-        x = fma2(bc(c[2]), y, x);
-    } else if (KIND == TK_SHI || KIND == TK_SHI_P || KIND == TK_SHI_Q) {
-        if (KIND == TK_SHI_P) {
-            x = mul2(bc(c[3]), x);
-            y = mul2(bc(c[4]), y);
-        } else if (KIND == TK_SHI_Q) {
-            x = mul2(pk(-c[3], c[3]), sw(x));      // x *= i sx
-            y = mul2(pk(-c[4], c[4]), sw(y));
-        }
-        x = fma_i(c[0], y, x);
-        y = fma_i(c[1], x, y);
-        x = fma_i(c[2], y, x);
-    } else if (KIND == TK_PERM_R) {
-        const f2 x0 = x;
-        x = mul2(bc(c[0]), y);
+__device__ __forceinline__ void butterfly_direct(f2& x, f2& y, const float (&c)[8]) {
+    const f2 x0 = x, y0 = y;
+    if (KIND == TK_PERM_R) {
+        x = mul2(bc(c[0]), y0);
         y = mul2(bc(c[1]), x0);
     } else if (KIND == TK_PERM_I) {
-        const f2 x0 = x;
-        x = mul2(pk(-c[0], c[0]), sw(y));
+        x = mul2(pk(-c[0], c[0]), sw(y0));
         y = mul2(pk(-c[1], c[1]), sw(x0));
     } else {
-        // general complex 2x2, c = {m00.re, m00.im, m01.re, m01.im, m10.re, m10.im, m11.re, m11.im}
-        const f2 x0 = x, y0 = y;
         f2 u = mul2(bc(c[0]), x0);
         u = fma_i(c[1], x0, u);
         u = fma2(bc(c[2]), y0, u);
@@ -200,42 +275,153 @@ __device__ __forceinline__ void butterfly(f2& x, f2& y, const float (&c)[8]) {
     }
 }
 
-template <int KIND, int TK, bool MASKED>
-__device__ __forceinline__ void apply_pairs(f2 (&a)[kRegs], const float (&c)[8], uint32_t pair_mask) {
+// J < 4: pairs whose pair-index bit J is set use ka, the others kb.  J == 4: generic 16-bit mask (uniform branches).
+template <int KIND, int TK, int J, bool PY>
+__device__ __forceinline__ void apply_shear(f2 (&a)[kRegs], const ShearCoef& ka, const ShearCoef& kb, uint32_t mask) {
 #pragma unroll
     for (int p = 0; p < kPairs; ++p) {
         const int k0 = ((p >> TK) << (TK + 1)) | (p & ((1 << TK) - 1));
         const int k1 = k0 | (1 << TK);
-        if (!MASKED || (pair_mask >> p & 1u)) butterfly<KIND>(a[k0], a[k1], c);
+        if (J < 4) shear<KIND, PY>(a[k0], a[k1], (p >> J & 1) ? ka : kb);
+        else shear<KIND, PY>(a[k0], a[k1], (mask >> p & 1u) ? ka : kb);
     }
 }
-
-template <int KIND, bool MASKED>
-__device__ __forceinline__ void apply_tk(f2 (&a)[kRegs], const float (&c)[8], uint32_t tk, uint32_t pair_mask) {
-    switch (tk) {
-        case 0: apply_pairs<KIND, 0, MASKED>(a, c, pair_mask); break;
-        case 1: apply_pairs<KIND, 1, MASKED>(a, c, pair_mask); break;
-        case 2: apply_pairs<KIND, 2, MASKED>(a, c, pair_mask); break;
-        case 3: apply_pairs<KIND, 3, MASKED>(a, c, pair_mask); break;
-        default: apply_pairs<KIND, 4, MASKED>(a, c, pair_mask); break;
+// factor kinds: MJ < 5: registers with bit MJ set; MJ == 5: all registers; 8..12: registers with bit MJ-8 clear;
+// otherwise a generic 32-bit mask (uniform branches)
+template <int KIND, int MJ>
+__device__ __forceinline__ void apply_factor(f2 (&a)[kRegs], float fr, float fi, uint32_t mask) {
+    // TK_PHASE multiplies by e^{i theta} as three shears on (re, im) — in place, no temporaries
+    // (fr = -tan(theta/2), fi = sin(theta), |theta| <= pi/2; a sign or modulus is a separate TK_SCALE_R)
+    const f2 re = bc(fr), ims = pk(-fr, fr);
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) {
+        const bool on = (MJ < 5) ? ((k >> MJ & 1) != 0) : (MJ == 5 ? true : (MJ >= 8 ? ((k >> (MJ - 8) & 1) == 0) : ((mask >> k & 1u) != 0)));
+        if (on) {
+            if (KIND == TK_PHASE) {
+                float xr = lo(a[k]), xi = hi(a[k]);
+                xr = fmaf(fr, xi, xr);
+                xi = fmaf(fi, xr, xi);
+                xr = fmaf(fr, xi, xr);
+                a[k] = pk(xr, xi);
+            } else if (KIND == TK_PHASE_N) {
+                // R(-v) = -R(v): start from the negated amplitude
+                float xr = lo(a[k]), xi = hi(a[k]);
+                xr = fmaf(-fr, xi, -xr);
+                xi = fmaf(fi, xr, -xi);
+                xr = fmaf(fr, xi, xr);
+                a[k] = pk(xr, xi);
+            } else if (KIND == TK_SCALE_R) {
+                a[k] = mul2(re, a[k]);
+            } else {
+                a[k] = mul2(ims, sw(a[k]));
+            }
+        }
     }
 }
-
-template <int KIND>
-__device__ __forceinline__ void apply_kind(f2 (&a)[kRegs], const float (&c)[8], uint32_t tk, uint32_t pair_mask) {
-    if (pair_mask == 0xffffu) apply_tk<KIND, false>(a, c, tk, pair_mask);
-    else apply_tk<KIND, true>(a, c, tk, pair_mask);
+template <int KIND, int TK>
+__device__ __forceinline__ void apply_direct(f2 (&a)[kRegs], const float (&c)[8], uint32_t mask) {
+#pragma unroll
+    for (int p = 0; p < kPairs; ++p) {
+        const int k0 = ((p >> TK) << (TK + 1)) | (p & ((1 << TK) - 1));
+        const int k1 = k0 | (1 << TK);
+        if (mask >> p & 1u) butterfly_direct<KIND>(a[k0], a[k1], c);
+    }
+}
+// Header of an op.  Each body reloads it for the NEXT op as soon as it has consumed the current
+// values, so the shared-memory latency hides behind the body's FP work and the loop carries no
+// register rotation.
+struct OpHead {
+    uint4 h;        // {word, mask, tpred, sx_a}
+    float4 a;
+};
+__device__ __forceinline__ void load_head(OpHead& hd, const DevOp& op) {
+    hd.h = *reinterpret_cast<const uint4*>(&op);
+    hd.a = *reinterpret_cast<const float4*>(&op.a[0]);
 }
 
-constexpr int tile_min_blocks(int T) { return T >= 13 ? 2 : 4; }
+template <int KIND, bool PY>
+__device__ __forceinline__ ShearCoef make_coef(float a, float b, float g, float sy, float sx, bool imag) {
+    ShearCoef k;
+    k.a = a; k.b = b; k.g = g;
+    if (KIND == TK_SHI && PY) {
+        k.sx = imag ? 0.f : sx; k.qx = imag ? sx : 0.f;
+        k.sy = imag ? 0.f : sy; k.qy = imag ? sy : 0.f;
+    } else {
+        k.sx = sx; k.sy = sy; k.qx = 0.f; k.qy = 0.f;
+    }
+    return k;
+}
 
-template <int T, int CAP>
-__global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_tile2(const __grid_constant__ PassParams<CAP> P) {
+template <int KIND, int TK, int J, bool PY>
+__device__ __forceinline__ void run_shear(f2 (&a)[kRegs], const DevOp& op, OpHead& hd, uint32_t tid) {
+    const uint32_t flags = hd.h.x >> 16, mask = hd.h.y;
+    ShearCoef ka = make_coef<KIND, PY>(hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0), kb = ka;
+    bool run = true;
+    if (flags & (TF_PRED | TF_REGMUX)) {
+        const float4 cb = *reinterpret_cast<const float4*>(&op.b[0]);
+        const ShearCoef kset_b = make_coef<KIND, PY>(cb.x, cb.y, cb.z, cb.w, PY ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0);
+        bool use_b;
+        run = op_predicate(op, flags, hd.h.z, tid, use_b);
+        if (use_b) ka = kset_b;
+        kb = ka;
+        if (flags & TF_REGMUX) kb = kset_b;
+    }
+    load_head(hd, (&op)[1]);
+    if (run) apply_shear<KIND, TK, J, PY>(a, ka, kb, mask);
+}
+template <int KIND, int TK>
+__device__ __forceinline__ void run_direct(f2 (&a)[kRegs], const DevOp& op, OpHead& hd, uint32_t tid) {
+    bool use_b;
+    const bool run = op_predicate(op, hd.h.x >> 16, hd.h.z, tid, use_b);
+    const float4 c1 = *reinterpret_cast<const float4*>(&op.b[0]);
+    const float c[8] = {hd.a.x, hd.a.y, hd.a.z, hd.a.w, c1.x, c1.y, c1.z, c1.w};
+    const uint32_t mask = hd.h.y;
+    load_head(hd, (&op)[1]);
+    if (run) apply_direct<KIND, TK>(a, c, mask);
+}
+template <int KIND, int MJ>
+__device__ __forceinline__ void run_factor(f2 (&a)[kRegs], const DevOp& op, OpHead& hd, uint32_t tid) {
+    bool use_b;
+    const bool run = op_predicate(op, hd.h.x >> 16, hd.h.z, tid, use_b);
+    const float fr = hd.a.x, fi = hd.a.y;
+    const uint32_t mask = hd.h.y;
+    load_head(hd, (&op)[1]);
+    if (run) apply_factor<KIND, MJ>(a, fr, fi, mask);
+}
+
+// dispatch on the low bits of `sub` with plain bit tests (nvcc lowers a switch to compare chains plus
+// small jump tables whose entries are again constant-bank loads)
+#define AQS_DISPATCH5(sub, F0, F1, F2, F3, F4)        \
+    do {                                              \
+        if ((sub) & 4u) { F4; }                       \
+        else if ((sub) & 2u) { if ((sub) & 1u) { F3; } else { F2; } } \
+        else { if ((sub) & 1u) { F1; } else { F0; } } \
+    } while (0)
+
+#ifndef AQS_TILE_MINB
+#define AQS_TILE_MINB 4
+#endif
+#ifndef AQS_TILE_MINB13
+#define AQS_TILE_MINB13 2
+#endif
+__host__ __device__ __forceinline__ constexpr int ctz_c(int i) { return (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : 4; }
+constexpr int tile_min_blocks(int T) { return T >= 13 ? AQS_TILE_MINB13 : AQS_TILE_MINB; }
+
+template <int T>
+__global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_tile2(const __grid_constant__ PassParams P) {
     constexpr int TB = T - kRegBits;   // thread bits
-    extern __shared__ __align__(16) float2 sm[];
+    extern __shared__ __align__(16) float2 sm[];                       // the tile, then the pass's DevOps
+    const DevOp* sops = reinterpret_cast<const DevOp*>(sm + (1u << T));
 
     const uint32_t tid = threadIdx.x;
     const uint64_t gbase = deposit_zeros((uint64_t)blockIdx.x, P.tile);
+    {
+        // descriptors -> shared memory (16 bytes per thread per step; the list ends with a sentinel)
+        const uint4* src = reinterpret_cast<const uint4*>(P.ops);
+        uint4* dst = reinterpret_cast<uint4*>(sm + (1u << T));
+        const uint32_t n16 = (P.n_ops + 1u) * (uint32_t)(sizeof(DevOp) / 16);
+        for (uint32_t i = tid; i < n16; i += (1u << TB)) dst[i] = __ldg(src + i);
+    }
 
     f2 a[kRegs];
     {
@@ -267,61 +453,88 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
                     rb ^= sg.rd_tcol[j];
                 }
             }
+            // Registers are visited in Gray-code order so that each shared-memory address is the
+            // previous one XOR one column: a single live address register instead of 32 (the
+            // unrolled address set was the kernel's register-pressure peak).
             __syncthreads();
+            {
+                uint32_t addr = wb;
 #pragma unroll
-            for (int k = 0; k < kRegs; ++k) {
-                uint32_t off = 0;
-#pragma unroll
-                for (int i = 0; i < kRegBits; ++i)
-                    if (k >> i & 1) off ^= sg.wr_rcol[i];
-                sm[wb ^ off] = make_float2(lo(a[k]), hi(a[k]));
+                for (int i = 0; i < kRegs; ++i) {
+                    const int k = i ^ (i >> 1);
+                    if (i) addr ^= sg.wr_rcol[ctz_c(i)];
+                    sm[addr] = make_float2(lo(a[k]), hi(a[k]));
+                }
             }
             __syncthreads();
+            {
+                uint32_t addr = rb;
 #pragma unroll
-            for (int k = 0; k < kRegs; ++k) {
-                uint32_t off = 0;
-#pragma unroll
-                for (int i = 0; i < kRegBits; ++i)
-                    if (k >> i & 1) off ^= sg.rd_rcol[i];
-                const float2 v = sm[rb ^ off];
-                a[k] = pk(v.x, v.y);
+                for (int i = 0; i < kRegs; ++i) {
+                    const int k = i ^ (i >> 1);
+                    if (i) addr ^= sg.rd_rcol[ctz_c(i)];
+                    const float2 v = sm[addr];
+                    a[k] = pk(v.x, v.y);
+                }
             }
         }
         const uint32_t first = sg.first_op, end = first + sg.n_ops;
+        if (first == end) continue;
+        if (s == 0) __syncthreads();          // descriptors visible (later segments pass the re-split barriers)
+        OpHead hd;
+        load_head(hd, sops[first]);
         for (uint32_t o = first; o < end; ++o) {
-            const TileOp& op = P.ops[o];
-            const bool mux = (op.flags & TF_MUX) != 0;
-            const bool blk_ok = (blockIdx.x & op.b_mask) == op.b_val;
-            if (!blk_ok && !mux) continue;                               // CTA-uniform
-            const bool ok = blk_ok && ((tid & op.t_mask) == op.t_val);
-            float c[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) c[i] = (mux && !ok) ? op.b[i] : op.a[i];
-            if (ok || mux) {
-                const uint32_t tk = op.tk, mask = op.mask;
-                switch (op.kind) {
-                    case TK_SHR: apply_kind<TK_SHR>(a, c, tk, mask); break;
-                    case TK_SHR_P: apply_kind<TK_SHR_P>(a, c, tk, mask); break;
-                    case TK_SHI: apply_kind<TK_SHI>(a, c, tk, mask); break;
-                    case TK_SHI_P: apply_kind<TK_SHI_P>(a, c, tk, mask); break;
-                    case TK_SHI_Q: apply_kind<TK_SHI_Q>(a, c, tk, mask); break;
-                    case TK_GEN: apply_kind<TK_GEN>(a, c, tk, mask); break;
-                    case TK_PERM_R: apply_kind<TK_PERM_R>(a, c, tk, mask); break;
-                    case TK_PERM_I: apply_kind<TK_PERM_I>(a, c, tk, mask); break;
-                    default: {
-                        const f2 re = bc(c[0]);
-                        const f2 im = pk(-c[1], c[1]);
-                        if (mask == 0xffffffffu) {
-#pragma unroll
-                            for (int k = 0; k < kRegs; ++k) a[k] = fma2(im, sw(a[k]), mul2(re, a[k]));
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < kRegs; ++k)
-                                if (mask >> k & 1u) a[k] = fma2(im, sw(a[k]), mul2(re, a[k]));
-                        }
-                    } break;
+            const DevOp& op = sops[o];          // every body leaves the header of op o + 1 in hd (the sentinel keeps it in bounds)
+            const uint32_t word = hd.h.x, sub = word & 7u, grp = (word >> 3) & 0x1fu;
+#define AQS_SH(K, TKV, PYV) AQS_DISPATCH5(sub, (run_shear<K, TKV, 0, PYV>(a, op, hd, tid)), (run_shear<K, TKV, 1, PYV>(a, op, hd, tid)), \
+                                     (run_shear<K, TKV, 2, PYV>(a, op, hd, tid)), (run_shear<K, TKV, 3, PYV>(a, op, hd, tid)), \
+                                     (run_shear<K, TKV, 4, PYV>(a, op, hd, tid)))
+#define AQS_SH5(K, PYV, g)                                                           \
+    do {                                                                             \
+        if ((g) & 4u) AQS_SH(K, 4, PYV);                                             \
+        else if ((g) & 2u) { if ((g) & 1u) AQS_SH(K, 3, PYV); else AQS_SH(K, 2, PYV); } \
+        else { if ((g) & 1u) AQS_SH(K, 1, PYV); else AQS_SH(K, 0, PYV); }            \
+    } while (0)
+#define AQS_DI(K) AQS_DISPATCH5(sub, (run_direct<K, 0>(a, op, hd, tid)), (run_direct<K, 1>(a, op, hd, tid)), \
+                                (run_direct<K, 2>(a, op, hd, tid)), (run_direct<K, 3>(a, op, hd, tid)), (run_direct<K, 4>(a, op, hd, tid)))
+#define AQS_FA(K, HI)                                                                                          \
+    do {                                                                                                       \
+        if (!(HI)) {                                                                                           \
+            if (sub & 4u) {                                                                                    \
+                if (sub & 2u) { if (sub & 1u) run_factor<K, 8>(a, op, hd, tid); else run_factor<K, 6>(a, op, hd, tid); } \
+                else { if (sub & 1u) run_factor<K, 5>(a, op, hd, tid); else run_factor<K, 4>(a, op, hd, tid); } \
+            } else if (sub & 2u) { if (sub & 1u) run_factor<K, 3>(a, op, hd, tid); else run_factor<K, 2>(a, op, hd, tid); } \
+            else { if (sub & 1u) run_factor<K, 1>(a, op, hd, tid); else run_factor<K, 0>(a, op, hd, tid); }    \
+        } else {                                                                                               \
+            if (sub & 2u) { if (sub & 1u) run_factor<K, 12>(a, op, hd, tid); else run_factor<K, 11>(a, op, hd, tid); } \
+            else { if (sub & 1u) run_factor<K, 10>(a, op, hd, tid); else run_factor<K, 9>(a, op, hd, tid); }    \
+        }                                                                                                      \
+    } while (0)
+            if (grp < 20u) {
+                // shears: grp = kind * 5 + tk (+ 10 with the y prescale)
+                if (grp < 10u) {
+                    if (grp < 5u) AQS_SH5(TK_SHR, false, grp);
+                    else AQS_SH5(TK_SHI, false, grp - 5u);
+                } else {
+                    if (grp < 15u) AQS_SH5(TK_SHR, true, grp - 10u);
+                    else AQS_SH5(TK_SHI, true, grp - 15u);
                 }
+            } else if (grp >= 23u) {
+                // factors: grp = 23 + (kind - TK_PHASE) * 2 + hi
+                const uint32_t g23 = grp - 23u;
+                if (g23 < 2u) AQS_FA(TK_PHASE, g23 & 1u);
+                else if (g23 < 4u) AQS_FA(TK_SCALE_R, g23 & 1u);
+                else if (g23 < 6u) AQS_FA(TK_SCALE_I, g23 & 1u);
+                else AQS_FA(TK_PHASE_N, g23 & 1u);
+            } else {
+                if (grp == 20u) AQS_DI(TK_GEN);
+                else if (grp == 21u) AQS_DI(TK_PERM_R);
+                else AQS_DI(TK_PERM_I);
             }
+#undef AQS_SH
+#undef AQS_SH5
+#undef AQS_DI
+#undef AQS_FA
         }
     }
 

@@ -12,7 +12,7 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaqs_engine.so")
+LIB_PATH = os.environ.get("AQS_ENGINE_LIB") or os.path.join(_HERE, "lib", "libaqs_engine.so")   # the override is for A/B builds of the engine
 
 OP_U2, OP_DIAG, OP_X, OP_SWAP = 0, 1, 2, 3
 PLAN_FUSE, PLAN_GRAPH = 1, 2

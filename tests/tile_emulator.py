@@ -12,8 +12,8 @@ import ctypes
 import numpy as np
 
 K_LANE, K_REG, K_MAX_THREAD_BITS, K_MAX_BITS = 5, 5, 8, 38
-SHR, SHR_P, SHI, SHI_P, SHI_Q, GEN, PHASE, PERM_R, PERM_I = range(9)
-TF_MUX = 1
+SHR, SHI, GEN, PERM_R, PERM_I, PHASE, SCALE_R, SCALE_I, PHASE_N = range(9)
+TF_MUX, TF_REGMUX, TF_PRED, TF_PY, TF_IMAG_A, TF_IMAG_B = 1, 2, 4, 8, 16, 32
 
 
 class BitList(ctypes.Structure):
@@ -36,9 +36,9 @@ class TileSeg(ctypes.Structure):
 
 
 class TileOp(ctypes.Structure):
-    _fields_ = [("kind", ctypes.c_uint8), ("tk", ctypes.c_uint8), ("flags", ctypes.c_uint8), ("pad0", ctypes.c_uint8),
-                ("mask", ctypes.c_uint32), ("t_mask", ctypes.c_uint16), ("t_val", ctypes.c_uint16),
-                ("b_mask", ctypes.c_uint32), ("b_val", ctypes.c_uint32), ("pad1", ctypes.c_uint32 * 3),
+    _fields_ = [("kind", ctypes.c_uint8), ("tk", ctypes.c_uint8), ("flags", ctypes.c_uint8), ("mj", ctypes.c_uint8),
+                ("mask", ctypes.c_uint32), ("t_mask", ctypes.c_uint16), ("t_val", ctypes.c_uint16), ("code", ctypes.c_uint32),
+                ("b_mask", ctypes.c_uint32), ("b_val", ctypes.c_uint32), ("sx", ctypes.c_float * 2),
                 ("a", ctypes.c_float * 8), ("b", ctypes.c_float * 8)]
 
 
@@ -83,25 +83,24 @@ def deposit(j, positions):
     return j
 
 
-def butterfly(kind, x, y, c):
-    """the kernel's in-place sequences, in float32 (tile_kernel.cuh butterfly<>)"""
+def butterfly(kind, x, y, c, py=False, sx=1.0, imag=False):
+    """the kernel's in-place sequences, in float32 (tile_kernel.cuh shear<> / butterfly_direct<>)"""
     f = np.float32
     c = [f(v) for v in c]
-    if kind in (SHR, SHR_P):
-        if kind == SHR_P:
-            x = x * c[3]
-            y = y * c[4]
+    if py:
+        if imag:
+            assert kind == SHI
+            x = x * (np.complex64(1j) * f(sx))
+            y = y * (np.complex64(1j) * c[3])
+        else:
+            x = x * f(sx)
+            y = y * c[3]
+    if kind == SHR:
         x = x + c[0] * y
         y = y + c[1] * x
         x = x + c[2] * y
-    elif kind in (SHI, SHI_P, SHI_Q):
+    elif kind == SHI:
         j = np.complex64(1j)
-        if kind == SHI_P:
-            x = x * c[3]
-            y = y * c[4]
-        elif kind == SHI_Q:
-            x = x * (j * c[3])
-            y = y * (j * c[4])
         x = x + (j * c[0]) * y
         y = y + (j * c[1]) * x
         x = x + (j * c[2]) * y
@@ -113,6 +112,41 @@ def butterfly(kind, x, y, c):
         m = [np.complex64(complex(c[2 * i], c[2 * i + 1])) for i in range(4)]
         x, y = m[0] * x + m[1] * y, m[2] * x + m[3] * y
     return x.astype(np.complex64), y.astype(np.complex64)
+
+
+def op_code(kind, tk, mj, flags):
+    """tile_kernel.cuh tile_op_code"""
+    if kind <= 1:
+        return ((kind * 5 + tk + (10 if flags & TF_PY else 0)) << 3) | mj
+    if kind <= 4:
+        return ((20 + kind - 2) << 3) | tk
+    pat = mj - 1 if mj >= 8 else mj
+    return ((23 + (kind - 5) * 2 + (pat >> 3)) << 3) | (pat & 7)
+
+
+def factor_mask(op):
+    """registers a factor op touches, from the compile-time pattern the kernel uses (must agree with op.mask)"""
+    k = np.arange(32)
+    if op.mj < 5:
+        sel = (k >> op.mj) & 1 == 1
+    elif op.mj == 5:
+        sel = np.ones(32, dtype=bool)
+    elif 8 <= op.mj <= 12:
+        sel = (k >> (op.mj - 8)) & 1 == 0
+    else:
+        sel = ((op.mask >> k) & 1).astype(bool)
+    assert np.array_equal(sel, ((op.mask >> k) & 1).astype(bool)), "mj pattern and mask disagree"
+    return sel
+
+
+def pair_uses_a(op, p):
+    """shears: does register pair p take coefficient set a (else set b)?"""
+    if op.mj < 4:
+        use = bool((p >> op.mj) & 1)
+        if op.flags & TF_REGMUX:
+            assert use == bool((op.mask >> p) & 1), "mj pattern and pair mask disagree"
+        return use
+    return bool((op.mask >> p) & 1)
 
 
 def check_swizzle(seg, T, stats):
@@ -170,26 +204,63 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
             thr_ok = (tid & np.uint32(op.t_mask)) == np.uint32(op.t_val)                   # (threads,)
             ok = blk_ok[:, None] & thr_ok[None, :]                                         # (tiles, threads)
             ca, cb = list(op.a), list(op.b)
-            if op.kind == PHASE:
+            assert op.code == (op_code(op.kind, op.tk, op.mj, op.flags) | (op.flags << 16)), "dispatch code does not match (kind, tk, mj, flags)"
+            assert bool(op.flags & TF_PRED) == bool(op.t_mask or op.b_mask), "TF_PRED must mirror the predicate fields"
+            if op.kind >= PHASE:
                 assert not mux
-                fac = np.complex64(complex(np.float32(ca[0]), np.float32(ca[1])))
-                sel = ((op.mask >> k) & 1).astype(bool)
+                if op.kind in (PHASE, PHASE_N):
+                    # three shears on (re, im): rotation by theta with c = {-tan(theta/2), sin(theta)}
+                    # (PHASE_N: of the negated amplitude)
+                    t, sn = np.float32(ca[0]), np.float32(ca[1])
+                    sgn = np.float32(-1.0 if op.kind == PHASE_N else 1.0)
+                    xr, xi = sgn * a.real.astype(np.float32), sgn * a.imag.astype(np.float32)
+                    xr = xr + t * xi
+                    xi = xi + sn * xr
+                    xr = xr + t * xi
+                    rot = (xr + 1j * xi).astype(np.complex64)
+                    sel = factor_mask(op)
+                    m = ok[:, :, None] & sel[None, None, :]
+                    a = np.where(m, rot, a)
+                    continue
+                elif op.kind == SCALE_R:
+                    fac = np.complex64(np.float32(ca[0]))
+                else:
+                    fac = np.complex64(1j) * np.float32(ca[0])
+                sel = factor_mask(op)
                 m = ok[:, :, None] & sel[None, None, :]
                 a = np.where(m, (a * fac).astype(np.complex64), a)
                 continue
             tk = op.tk
+            shear = op.kind <= SHI
+            regmux = bool(op.flags & TF_REGMUX)
+            assert not (mux and regmux)
+            if not shear:
+                assert not mux and not regmux
             for p in range(16):
-                if not (op.mask >> p) & 1:
-                    continue
                 k0 = ((p >> tk) << (tk + 1)) | (p & ((1 << tk) - 1))
                 k1 = k0 | (1 << tk)
                 x, y = a[:, :, k0], a[:, :, k1]
-                xa, ya = butterfly(op.kind, x, y, ca)
-                if mux:
-                    xb, yb = butterfly(op.kind, x, y, cb)
+                if not shear:
+                    if not (op.mask >> p) & 1:
+                        continue
+                    xa, ya = butterfly(op.kind, x, y, ca)
+                    a[:, :, k0] = np.where(ok, xa, x)
+                    a[:, :, k1] = np.where(ok, ya, y)
+                    continue
+                # kernel: ka = (mux && !ok) ? b : a;  kb = regmux ? b : ka;  pair subset picks ka / kb;
+                # threads with !ok and no mux skip the op
+                py = bool(op.flags & TF_PY)
+                xa, ya = butterfly(op.kind, x, y, ca, py, op.sx[0], bool(op.flags & TF_IMAG_A))
+                xb, yb = butterfly(op.kind, x, y, cb, py, op.sx[1], bool(op.flags & TF_IMAG_B))
+                if regmux:
+                    xs, ys = (xa, ya) if pair_uses_a(op, p) else (xb, yb)
+                    a[:, :, k0] = np.where(ok, xs, x)
+                    a[:, :, k1] = np.where(ok, ys, y)
+                elif mux:
                     a[:, :, k0] = np.where(ok, xa, xb)
                     a[:, :, k1] = np.where(ok, ya, yb)
                 else:
+                    assert op.mask == 0xffff
                     a[:, :, k0] = np.where(ok, xa, x)
                     a[:, :, k1] = np.where(ok, ya, y)
 
