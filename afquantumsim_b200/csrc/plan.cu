@@ -668,19 +668,28 @@ struct Emitter {
                 t.sx[0] = 1.f;
                 if (t.flags & TF_IMAG_A) t.flags = (uint8_t)((t.flags & ~TF_IMAG_A) | TF_IMAG_B);
                 t.mask = pair_mask(tk, rm, rm);
-            } else {
-                t.flags |= TF_REGMUX;
-                t.mj = 4;                       // generic mask
-                for (int i = 0; i < 8; ++i) t.b[i] = 0.f;
-                t.b[3] = 1.f;
             }
+            // (several controls on register bits never reach here: emit_matrix sends them down the direct path)
         }
         push(t);
     }
     void emit_matrix(const cd* M, int bit, int tk, uint64_t cm, uint64_t cv) const {
         if (mat_is_identity(M)) return;
-        const Decomp d = decompose(M);
+        Decomp d = decompose(M);
         (void)bit;
+        if (d.kind <= TK_SHI) {
+            // shear bodies resolve pair subsets at compile time (one control on a register bit at most);
+            // with more, fall back to the direct 2x2, which takes any pair mask
+            TileOp probe;
+            std::memset(&probe, 0, sizeof probe);
+            uint32_t rm, rv;
+            select(cm, cv, rm, rv, probe);
+            if (popc(rm) >= 2) {
+                d = Decomp();
+                d.kind = TK_GEN;
+                for (int i = 0; i < 4; ++i) { d.c[2 * i] = (float)M[i].real(); d.c[2 * i + 1] = (float)M[i].imag(); }
+            }
+        }
         emit_butterfly(d, nullptr, -1, tk, cm, cv);
     }
     void emit(const POp& o, cd& pass_scale) const {

@@ -275,15 +275,15 @@ __device__ __forceinline__ void butterfly_direct(f2& x, f2& y, const float (&c)[
     }
 }
 
-// J < 4: pairs whose pair-index bit J is set use ka, the others kb.  J == 4: generic 16-bit mask (uniform branches).
+// Pairs whose pair-index bit J is set use ka, the others kb (ops that need any other subset of the
+// pairs are emitted as TK_GEN by the planner).
 template <int KIND, int TK, int J, bool PY>
-__device__ __forceinline__ void apply_shear(f2 (&a)[kRegs], const ShearCoef& ka, const ShearCoef& kb, uint32_t mask) {
+__device__ __forceinline__ void apply_shear(f2 (&a)[kRegs], const ShearCoef& ka, const ShearCoef& kb) {
 #pragma unroll
     for (int p = 0; p < kPairs; ++p) {
         const int k0 = ((p >> TK) << (TK + 1)) | (p & ((1 << TK) - 1));
         const int k1 = k0 | (1 << TK);
-        if (J < 4) shear<KIND, PY>(a[k0], a[k1], (p >> J & 1) ? ka : kb);
-        else shear<KIND, PY>(a[k0], a[k1], (mask >> p & 1u) ? ka : kb);
+        shear<KIND, PY>(a[k0], a[k1], (p >> J & 1) ? ka : kb);
     }
 }
 // factor kinds: MJ < 5: registers with bit MJ set; MJ == 5: all registers; 8..12: registers with bit MJ-8 clear;
@@ -339,27 +339,25 @@ __device__ __forceinline__ void load_head(OpHead& hd, const DevOp& op) {
     hd.a = *reinterpret_cast<const float4*>(&op.a[0]);
 }
 
-template <int KIND, bool PY>
-__device__ __forceinline__ ShearCoef make_coef(float a, float b, float g, float sy, float sx, bool imag) {
+// Class preludes, one copy each in the interpreter loop: predicate, coefficient sets, header of the next op.
+__device__ __forceinline__ ShearCoef make_coef(bool shi_py, float a, float b, float g, float sy, float sx, bool imag) {
     ShearCoef k;
     k.a = a; k.b = b; k.g = g;
-    if (KIND == TK_SHI && PY) {
-        k.sx = imag ? 0.f : sx; k.qx = imag ? sx : 0.f;
-        k.sy = imag ? 0.f : sy; k.qy = imag ? sy : 0.f;
-    } else {
-        k.sx = sx; k.sy = sy; k.qx = 0.f; k.qy = 0.f;
-    }
+    const bool im = shi_py && imag;
+    k.sx = im ? 0.f : sx; k.qx = im ? sx : 0.f;
+    k.sy = im ? 0.f : sy; k.qy = im ? sy : 0.f;
     return k;
 }
-
-template <int KIND, int TK, int J, bool PY>
-__device__ __forceinline__ void run_shear(f2 (&a)[kRegs], const DevOp& op, OpHead& hd, uint32_t tid) {
-    const uint32_t flags = hd.h.x >> 16, mask = hd.h.y;
-    ShearCoef ka = make_coef<KIND, PY>(hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0), kb = ka;
+__device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint32_t tid, ShearCoef& ka, ShearCoef& kb) {
+    const uint32_t flags = hd.h.x >> 16;
+    const bool py = (flags & TF_PY) != 0;
+    const bool shi_py = py && (((hd.h.x >> 3) & 0x1fu) >= 15u);
+    ka = make_coef(shi_py, hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0);
+    kb = ka;
     bool run = true;
     if (flags & (TF_PRED | TF_REGMUX)) {
         const float4 cb = *reinterpret_cast<const float4*>(&op.b[0]);
-        const ShearCoef kset_b = make_coef<KIND, PY>(cb.x, cb.y, cb.z, cb.w, PY ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0);
+        const ShearCoef kset_b = make_coef(shi_py, cb.x, cb.y, cb.z, cb.w, py ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0);
         bool use_b;
         run = op_predicate(op, flags, hd.h.z, tid, use_b);
         if (use_b) ka = kset_b;
@@ -367,26 +365,7 @@ __device__ __forceinline__ void run_shear(f2 (&a)[kRegs], const DevOp& op, OpHea
         if (flags & TF_REGMUX) kb = kset_b;
     }
     load_head(hd, (&op)[1]);
-    if (run) apply_shear<KIND, TK, J, PY>(a, ka, kb, mask);
-}
-template <int KIND, int TK>
-__device__ __forceinline__ void run_direct(f2 (&a)[kRegs], const DevOp& op, OpHead& hd, uint32_t tid) {
-    bool use_b;
-    const bool run = op_predicate(op, hd.h.x >> 16, hd.h.z, tid, use_b);
-    const float4 c1 = *reinterpret_cast<const float4*>(&op.b[0]);
-    const float c[8] = {hd.a.x, hd.a.y, hd.a.z, hd.a.w, c1.x, c1.y, c1.z, c1.w};
-    const uint32_t mask = hd.h.y;
-    load_head(hd, (&op)[1]);
-    if (run) apply_direct<KIND, TK>(a, c, mask);
-}
-template <int KIND, int MJ>
-__device__ __forceinline__ void run_factor(f2 (&a)[kRegs], const DevOp& op, OpHead& hd, uint32_t tid) {
-    bool use_b;
-    const bool run = op_predicate(op, hd.h.x >> 16, hd.h.z, tid, use_b);
-    const float fr = hd.a.x, fi = hd.a.y;
-    const uint32_t mask = hd.h.y;
-    load_head(hd, (&op)[1]);
-    if (run) apply_factor<KIND, MJ>(a, fr, fi, mask);
+    return run;
 }
 
 // dispatch on the low bits of `sub` with plain bit tests (nvcc lowers a switch to compare chains plus
@@ -486,32 +465,36 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
         for (uint32_t o = first; o < end; ++o) {
             const DevOp& op = sops[o];          // every body leaves the header of op o + 1 in hd (the sentinel keeps it in bounds)
             const uint32_t word = hd.h.x, sub = word & 7u, grp = (word >> 3) & 0x1fu;
-#define AQS_SH(K, TKV, PYV) AQS_DISPATCH5(sub, (run_shear<K, TKV, 0, PYV>(a, op, hd, tid)), (run_shear<K, TKV, 1, PYV>(a, op, hd, tid)), \
-                                     (run_shear<K, TKV, 2, PYV>(a, op, hd, tid)), (run_shear<K, TKV, 3, PYV>(a, op, hd, tid)), \
-                                     (run_shear<K, TKV, 4, PYV>(a, op, hd, tid)))
+#define AQS_SH(K, TKV, PYV)                                                          \
+    do {                                                                             \
+        if (sub & 2u) { if (sub & 1u) apply_shear<K, TKV, 3, PYV>(a, ka, kb); else apply_shear<K, TKV, 2, PYV>(a, ka, kb); } \
+        else { if (sub & 1u) apply_shear<K, TKV, 1, PYV>(a, ka, kb); else apply_shear<K, TKV, 0, PYV>(a, ka, kb); } \
+    } while (0)
 #define AQS_SH5(K, PYV, g)                                                           \
     do {                                                                             \
         if ((g) & 4u) AQS_SH(K, 4, PYV);                                             \
         else if ((g) & 2u) { if ((g) & 1u) AQS_SH(K, 3, PYV); else AQS_SH(K, 2, PYV); } \
         else { if ((g) & 1u) AQS_SH(K, 1, PYV); else AQS_SH(K, 0, PYV); }            \
     } while (0)
-#define AQS_DI(K) AQS_DISPATCH5(sub, (run_direct<K, 0>(a, op, hd, tid)), (run_direct<K, 1>(a, op, hd, tid)), \
-                                (run_direct<K, 2>(a, op, hd, tid)), (run_direct<K, 3>(a, op, hd, tid)), (run_direct<K, 4>(a, op, hd, tid)))
+#define AQS_DI(K) AQS_DISPATCH5(sub, (apply_direct<K, 0>(a, c, mask)), (apply_direct<K, 1>(a, c, mask)), \
+                                (apply_direct<K, 2>(a, c, mask)), (apply_direct<K, 3>(a, c, mask)), (apply_direct<K, 4>(a, c, mask)))
 #define AQS_FA(K, HI)                                                                                          \
     do {                                                                                                       \
         if (!(HI)) {                                                                                           \
             if (sub & 4u) {                                                                                    \
-                if (sub & 2u) { if (sub & 1u) run_factor<K, 8>(a, op, hd, tid); else run_factor<K, 6>(a, op, hd, tid); } \
-                else { if (sub & 1u) run_factor<K, 5>(a, op, hd, tid); else run_factor<K, 4>(a, op, hd, tid); } \
-            } else if (sub & 2u) { if (sub & 1u) run_factor<K, 3>(a, op, hd, tid); else run_factor<K, 2>(a, op, hd, tid); } \
-            else { if (sub & 1u) run_factor<K, 1>(a, op, hd, tid); else run_factor<K, 0>(a, op, hd, tid); }    \
+                if (sub & 2u) { if (sub & 1u) apply_factor<K, 8>(a, fr, fi, mask); else apply_factor<K, 6>(a, fr, fi, mask); } \
+                else { if (sub & 1u) apply_factor<K, 5>(a, fr, fi, mask); else apply_factor<K, 4>(a, fr, fi, mask); } \
+            } else if (sub & 2u) { if (sub & 1u) apply_factor<K, 3>(a, fr, fi, mask); else apply_factor<K, 2>(a, fr, fi, mask); } \
+            else { if (sub & 1u) apply_factor<K, 1>(a, fr, fi, mask); else apply_factor<K, 0>(a, fr, fi, mask); }    \
         } else {                                                                                               \
-            if (sub & 2u) { if (sub & 1u) run_factor<K, 12>(a, op, hd, tid); else run_factor<K, 11>(a, op, hd, tid); } \
-            else { if (sub & 1u) run_factor<K, 10>(a, op, hd, tid); else run_factor<K, 9>(a, op, hd, tid); }    \
+            if (sub & 2u) { if (sub & 1u) apply_factor<K, 12>(a, fr, fi, mask); else apply_factor<K, 11>(a, fr, fi, mask); } \
+            else { if (sub & 1u) apply_factor<K, 10>(a, fr, fi, mask); else apply_factor<K, 9>(a, fr, fi, mask); }    \
         }                                                                                                      \
     } while (0)
             if (grp < 20u) {
-                // shears: grp = kind * 5 + tk (+ 10 with the y prescale)
+                // shears: grp = kind * 5 + tk (+ 10 with a prescale)
+                ShearCoef ka, kb;
+                if (!shear_prelude(op, hd, tid, ka, kb)) continue;
                 if (grp < 10u) {
                     if (grp < 5u) AQS_SH5(TK_SHR, false, grp);
                     else AQS_SH5(TK_SHI, false, grp - 5u);
@@ -519,17 +502,30 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
                     if (grp < 15u) AQS_SH5(TK_SHR, true, grp - 10u);
                     else AQS_SH5(TK_SHI, true, grp - 15u);
                 }
-            } else if (grp >= 23u) {
-                // factors: grp = 23 + (kind - TK_PHASE) * 2 + hi
-                const uint32_t g23 = grp - 23u;
-                if (g23 < 2u) AQS_FA(TK_PHASE, g23 & 1u);
-                else if (g23 < 4u) AQS_FA(TK_SCALE_R, g23 & 1u);
-                else if (g23 < 6u) AQS_FA(TK_SCALE_I, g23 & 1u);
-                else AQS_FA(TK_PHASE_N, g23 & 1u);
             } else {
-                if (grp == 20u) AQS_DI(TK_GEN);
-                else if (grp == 21u) AQS_DI(TK_PERM_R);
-                else AQS_DI(TK_PERM_I);
+                bool use_b;
+                const bool run = op_predicate(op, word >> 16, hd.h.z, tid, use_b);
+                const uint32_t mask = hd.h.y;
+                const float4 c0 = hd.a;
+                if (grp >= 23u) {
+                    // factors: grp = 23 + (kind - TK_PHASE) * 2 + hi
+                    load_head(hd, (&op)[1]);
+                    if (!run) continue;
+                    const float fr = c0.x, fi = c0.y;
+                    const uint32_t g23 = grp - 23u;
+                    if (g23 < 2u) AQS_FA(TK_PHASE, g23 & 1u);
+                    else if (g23 < 4u) AQS_FA(TK_SCALE_R, g23 & 1u);
+                    else if (g23 < 6u) AQS_FA(TK_SCALE_I, g23 & 1u);
+                    else AQS_FA(TK_PHASE_N, g23 & 1u);
+                } else {
+                    const float4 c1 = *reinterpret_cast<const float4*>(&op.b[0]);
+                    load_head(hd, (&op)[1]);
+                    if (!run) continue;
+                    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    if (grp == 20u) AQS_DI(TK_GEN);
+                    else if (grp == 21u) AQS_DI(TK_PERM_R);
+                    else AQS_DI(TK_PERM_I);
+                }
             }
 #undef AQS_SH
 #undef AQS_SH5

@@ -141,12 +141,11 @@ def factor_mask(op):
 
 def pair_uses_a(op, p):
     """shears: does register pair p take coefficient set a (else set b)?"""
-    if op.mj < 4:
-        use = bool((p >> op.mj) & 1)
-        if op.flags & TF_REGMUX:
-            assert use == bool((op.mask >> p) & 1), "mj pattern and pair mask disagree"
-        return use
-    return bool((op.mask >> p) & 1)
+    assert op.mj < 4, "shear ops resolve pair subsets at compile time"
+    use = bool((p >> op.mj) & 1)
+    if op.flags & TF_REGMUX:
+        assert use == bool((op.mask >> p) & 1), "mj pattern and pair mask disagree"
+    return use
 
 
 def check_swizzle(seg, T, stats):
