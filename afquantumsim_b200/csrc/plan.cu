@@ -106,6 +106,10 @@ struct Decomp {
     float c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double sx = 1.0, sy = 1.0;   // shears only: factors applied first to the target-bit-0 / target-bit-1 amplitudes
     bool pre_imag = false;       // the prescale is (i*sx, i*sy)
+    double rho = 1.0;            // shears only: common modulus, M = rho * (shears * prescale).  The reference's
+                                 // float matrices are orthogonal only to ~1e-7 (h = 0.70710677f, fl(cos)^2 + fl(sin)^2 != 1)
+                                 // but they ARE exact scalar multiples of a rotation / reflection: rho carries the
+                                 // scalar, so the fused path drifts in norm exactly like the reference does
     int cost = 8;                // FFMA2 per amplitude pair, prescale included
 };
 
@@ -160,6 +164,7 @@ static Decomp decompose(const cd* M) {
     if (std::fabs(A * A + C * C - 1.0) < 2e-6 && std::fabs(B * B + D * D - 1.0) < 2e-6 && std::fabs(orth) < 2e-6) {
         sx = (A >= 0 ? 1.0 : -1.0);
         sy = (det >= 0 ? sx : -sx);
+        d.rho = std::sqrt(std::fabs(det));
         const double phi = std::atan2(C / sx, A / sx);      // |phi| <= pi/2
         b = std::sin(phi);
         a = g = (cls == 0 ? -1.0 : 1.0) * std::tan(0.5 * phi);
@@ -673,10 +678,16 @@ struct Emitter {
         }
         push(t);
     }
-    void emit_matrix(const cd* M, int bit, int tk, uint64_t cm, uint64_t cv) const {
+    void emit_matrix(const cd* M, int bit, int tk, uint64_t cm, uint64_t cv, cd* pass_scale = nullptr) const {
         if (mat_is_identity(M)) return;
         Decomp d = decompose(M);
         (void)bit;
+        if (d.kind <= TK_SHI && d.rho != 1.0) {
+            // the common modulus of an uncontrolled op is a global factor; a controlled one keeps it in its prescale
+            if (pass_scale) *pass_scale *= d.rho;
+            else { d.sx *= d.rho; d.sy *= d.rho; }
+            d.rho = 1.0;
+        }
         if (d.kind <= TK_SHI) {
             // shear bodies resolve pair subsets at compile time (one control on a register bit at most);
             // with more, fall back to the direct 2x2, which takes any pair mask
@@ -721,7 +732,7 @@ struct Emitter {
             }
         }
         if (o.mux < 0) {
-            emit_matrix(m0, o.p, tk, o.cmask, o.cval);
+            emit_matrix(m0, o.p, tk, o.cmask, o.cval, o.cmask == 0 ? &pass_scale : nullptr);
             return;
         }
         const uint64_t mb = 1ull << o.mux;
@@ -731,6 +742,11 @@ struct Emitter {
         if (mat_is_identity(m1) && d0.kind <= TK_SHI) { d1 = Decomp(); d1.kind = d0.kind; d1.cost = 0; }
         // (a default Decomp has zero shear coefficients and sx = sy = 1: the identity)
         if (o.cmask == 0 && d0.kind == d1.kind && d0.kind <= TK_SHI) {
+            // common modulus -> pass-wide scale; a branch whose modulus differs keeps the ratio in its prescale
+            const double common = d0.rho;
+            pass_scale *= common;
+            d1.sx *= d1.rho / common; d1.sy *= d1.rho / common;
+            d0.rho = d1.rho = 1.0;
             emit_butterfly(d1, &d0, o.mux, tk, 0, 0);
             return;
         }

@@ -1,0 +1,91 @@
+"""CPU: the fusion planner's launch descriptors, executed by the numpy emulator of the tile kernel
+(tests/tile_emulator.py), against the oracle.  This pins everything about a fused plan except the
+CUDA code itself: op rewriting (merges, CX folded into multiplexed rotations), pass/segment grouping,
+layouts, shared-memory swizzles, predicates, in-place shear decompositions.  The GPU tests then
+compare the real kernel with the same oracle."""
+import numpy as np
+import pytest
+
+from afquantumsim_b200 import engine as eng
+from afquantumsim_b200 import workloads as wl
+from oracle import oracle as orc
+from tests import tile_emulator as te
+from tests.lowering import lower_array
+from tests.test_gpu_engine import random_circuit
+
+TOL = 1e-5
+
+
+def random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    a = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)).astype(np.complex64)
+    return (a / np.float32(np.sqrt(orc.norm2(a)))).astype(np.complex64)
+
+
+def emulate(n, circ, init, stats=None):
+    plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)
+    assert plan.info()["n_fused_passes"] > 0
+    return te.run_plan(plan, init, stats)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_circuits_all_gate_classes(seed):
+    n = 10 + seed % 4
+    circ = random_circuit(n, 70, 1000 + seed)
+    init = random_state(n, seed)
+    stats = {}
+    got = emulate(n, circ, init, stats)
+    assert orc.rel_l2(got, orc.simulate(init.copy(), circ)) < TOL
+    assert stats.get("conflicts", 0) == 0, "a re-split swizzle leaves shared-memory bank conflicts"
+
+
+@pytest.mark.parametrize("n,depth", [(10, 4), (12, 8), (14, 10)])
+def test_brickwork(n, depth):
+    circ = orc.Circ(n, wl.brickwork(n, depth))
+    init = random_state(n, n)
+    assert orc.rel_l2(emulate(n, circ, init), orc.simulate(init.copy(), circ)) < TOL
+
+
+@pytest.mark.parametrize("n", [10, 13])
+def test_qft_and_grover(n):
+    init = random_state(n, 7)
+    circ = orc.Circ(n, wl.qft(n))
+    assert orc.rel_l2(emulate(n, circ, init), orc.simulate(init.copy(), circ)) < TOL
+    circ = orc.grover_search(n, orc.grover_oracle(n, 5), 3)
+    assert orc.rel_l2(emulate(n, circ, init), orc.simulate(init.copy(), circ)) < TOL
+
+
+def test_ghz_is_exact():
+    for n in (10, 12, 14):
+        circ = orc.Circ(n, wl.ghz(n))
+        got = emulate(n, circ, orc.new_state(n))
+        assert np.array_equal(got, orc.simulate(orc.new_state(n), circ))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_permutation_circuits_are_exact(seed):
+    """X / CX / Swap / CCNot / CSwap only move amplitudes: the fused path must not round them"""
+    n = 12
+    r = np.random.default_rng(seed)
+    gates = []
+    for _ in range(50):
+        q = [int(x) for x in r.choice(n, 3, replace=False)]
+        gates.append([("X", q[0]), ("CX", q[0], q[1]), ("Swap", q[0], q[1]), ("CCNot", q[0], q[1], q[2]),
+                      ("CSwap", q[0], q[1], q[2])][int(r.integers(5))])
+    circ = orc.Circ(n, gates)
+    init = random_state(n, seed)
+    assert np.array_equal(emulate(n, circ, init), orc.simulate(init.copy(), circ))
+
+
+def test_cx_folds_into_rotations():
+    """brickwork: every CX next to a rotation on its target becomes part of a multiplexed shear op"""
+    n = 14
+    plan = eng.Plan(n, lower_array(orc.Circ(n, wl.brickwork(n, 10))), eng.PLAN_FUSE)
+    kinds = []
+    for i in range(plan.info()["n_fused_passes"]):
+        _, _, ops = te.parse(plan.export_pass(i))
+        kinds += [op.kind for op in ops]
+    n_gates = len(wl.brickwork(n, 10))
+    assert len(kinds) < 0.75 * n_gates, (len(kinds), n_gates)
+    assert sum(k in (te.PERM_R, te.PERM_I) for k in kinds) < 0.15 * len(kinds)
+    assert sum(k == te.GEN for k in kinds) < 0.1 * len(kinds)      # edge qubits: rotations with no CX between them merge
