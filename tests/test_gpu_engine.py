@@ -307,6 +307,49 @@ def test_brickwork_matches_oracle(n, fuse):
     assert np.array_equal(s2.sample(u), ref)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_fused_permutation_circuits_are_exact(seed):
+    """X / CX / Swap / CCNot / CSwap only move amplitudes: the tile kernel's TK_PERM path must not round them"""
+    n = 14
+    r = np.random.default_rng(seed)
+    gates = []
+    for _ in range(80):
+        q = [int(x) for x in r.choice(n, 3, replace=False)]
+        gates.append([("X", q[0]), ("CX", q[0], q[1]), ("Swap", q[0], q[1]), ("CCNot", q[0], q[1], q[2]),
+                      ("CSwap", q[0], q[1], q[2])][int(r.integers(5))])
+    circ = orc.Circ(n, gates)
+    init = random_state(n, seed)
+    assert np.array_equal(gpu_run(n, init, circ, fuse=True), orc.simulate(init.copy(), circ))
+
+
+@pytest.mark.parametrize("tile_bits", [10, 11, 13])
+def test_other_tile_sizes(tile_bits, monkeypatch):
+    """the tile kernel is instantiated for 10..13 tile bits; AQS_TILE_BITS selects one at plan time"""
+    monkeypatch.setenv("AQS_TILE_BITS", str(tile_bits))
+    n = 16
+    circ = random_circuit(n, 150, 40 + tile_bits)
+    init = random_state(n, tile_bits)
+    plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)
+    assert plan.info()["tile_bits"] == tile_bits
+    s = eng.State(n)
+    s.upload(init)
+    s.run(plan)
+    assert orc.rel_l2(s.download(), orc.simulate(init.copy(), circ)) < TOL
+
+
+def test_long_circuit_on_one_tile_splits_passes():
+    """n = tile size: everything fits one tile, so passes are cut by the per-pass op budget"""
+    n = 12
+    circ = random_circuit(n, 1500, 77)
+    init = random_state(n, 5)
+    plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)
+    assert plan.info()["n_fused_passes"] >= 3
+    s = eng.State(n)
+    s.upload(init)
+    s.run(plan)
+    assert orc.rel_l2(s.download(), orc.simulate(init.copy(), circ)) < 3 * TOL      # 1500 gates of fp32 rounding
+
+
 def test_error_paths():
     s = eng.State(4)
     with pytest.raises(eng.EngineError):
