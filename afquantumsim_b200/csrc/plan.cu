@@ -765,7 +765,7 @@ static int build_fused(aqs_plan_s* p) {
     const int TB = T - kRegBits;
     const uint64_t all_bits = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     const uint64_t low_mask = (1ull << kLaneBits) - 1ull;
-    const size_t kMaxTake = kOpsLarge / 2;     // every planner op emits at most two tile ops
+    const size_t kMaxTake = kOpsLarge;         // upper bound only: the emission loop enforces the descriptor budget
 
     std::vector<POp> ops = simplify(n, p->ops);
     if (std::getenv("AQS_PLAN_DUMP") && std::atoi(std::getenv("AQS_PLAN_DUMP")) > 2)
@@ -846,7 +846,20 @@ static int build_fused(aqs_plan_s* p) {
             Layout L = make_layout(T, regs);
             const uint32_t first = (uint32_t)fp.ops.size();
             em.L = &L;
-            for (int idx : seg_taken) em.emit(ops[idx], pass_scale);
+            // emit until the pass's descriptor budget is nearly used (an op emits at most 4 tile ops);
+            // whatever is left goes back to the candidates, in program order
+            bool full = false;
+            for (size_t i = 0; i < seg_taken.size(); ++i) {
+                if (fp.ops.size() + 4 > (size_t)kOpsLarge) {
+                    unplaced.assign(seg_taken.begin() + i, seg_taken.end());
+                    std::vector<int> merged(unplaced.size() + seg_rest.size());
+                    std::merge(unplaced.begin(), unplaced.end(), seg_rest.begin(), seg_rest.end(), merged.begin());
+                    unplaced.swap(merged);
+                    full = true;
+                    break;
+                }
+                em.emit(ops[seg_taken[i]], pass_scale);
+            }
             const uint32_t cnt = (uint32_t)fp.ops.size() - first;
             if (!layouts.empty() && layouts.back().same(L)) {
                 ranges.back().second += cnt;
@@ -854,6 +867,7 @@ static int build_fused(aqs_plan_s* p) {
                 layouts.push_back(L);
                 ranges.push_back({first, cnt});
             }
+            if (full) break;
             seg_cand.swap(seg_rest);
         }
         if (fp.ops.size() > (size_t)kOpsLarge) return fail(AQS_ERR_STATE, "fusion planner overflowed a pass");

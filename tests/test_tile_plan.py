@@ -89,3 +89,16 @@ def test_cx_folds_into_rotations():
     assert len(kinds) < 0.75 * n_gates, (len(kinds), n_gates)
     assert sum(k in (te.PERM_R, te.PERM_I) for k in kinds) < 0.15 * len(kinds)
     assert sum(k == te.GEN for k in kinds) < 0.1 * len(kinds)      # edge qubits: rotations with no CX between them merge
+
+
+def test_descriptor_budget_splits_passes():
+    """a 12-qubit state is one tile: 468 gates exceed the per-pass descriptor budget and must split cleanly"""
+    n = 12
+    gates = []
+    for _ in range(6):
+        gates += wl.qft(n)
+    circ = orc.Circ(n, gates)
+    plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)
+    assert plan.info()["n_fused_passes"] >= 2
+    init = random_state(n, 3)
+    assert orc.rel_l2(te.run_plan(plan, init), orc.simulate(init.copy(), circ)) < TOL
