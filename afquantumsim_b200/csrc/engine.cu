@@ -16,6 +16,7 @@
 #include "engine_internal.h"
 #include "gate_kernels.cuh"
 #include "measure_kernels.cuh"
+#include "peer_kernels.cuh"
 
 namespace aqs {
 
@@ -306,7 +307,9 @@ int aqs_engine_init(int device) {
     return AQS_OK;
 }
 
+int aqs_ipc_close_all(void);
 int aqs_engine_shutdown(void) {
+    aqs_ipc_close_all();
     pool_release_all();
     g_inited = false;
     return AQS_OK;
@@ -643,6 +646,89 @@ int aqs_sample_fixed(aqs_state_t s, const uint64_t* u, uint64_t n, uint64_t* out
 int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     REQUIRE(hist, "null histogram");
     return sample_impl(s, u, nullptr, n, nullptr, hist);
+}
+
+// ---- peer memory (sharded states on one NVLink / NVSwitch node) ---------------
+// Opened handles are cached for the life of the engine: state buffers are pooled, so the same
+// allocations (and handles) come back run after run, and cudaIpcOpenMemHandle / Close cost milliseconds.
+struct IpcEntry { cudaIpcMemHandle_t h; void* p; };
+static std::vector<IpcEntry> g_ipc;
+
+int aqs_state_ipc_export(aqs_state_t s, void* handle_out) {
+    REQUIRE_INIT();
+    REQUIRE(s && handle_out, "null argument");
+    REQUIRE(s->own_memory, "only engine-allocated states can be exported (the buffer must be the base of its allocation)");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->d));
+    static_assert(sizeof(cudaIpcMemHandle_t) == AQS_IPC_HANDLE_BYTES, "IPC handle size");
+    std::memcpy(handle_out, &h, sizeof h);
+    return AQS_OK;
+}
+
+int aqs_ipc_open(const void* handle, void** peer_ptr) {
+    REQUIRE_INIT();
+    REQUIRE(handle && peer_ptr, "null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& e : g_ipc)
+        if (std::memcmp(&e.h, &h, sizeof h) == 0) { *peer_ptr = e.p; return AQS_OK; }
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaIpcOpenMemHandle", __LINE__);
+    g_ipc.push_back({h, p});
+    *peer_ptr = p;
+    return AQS_OK;
+}
+
+int aqs_ipc_close_all(void) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& e : g_ipc) cudaIpcCloseMemHandle(e.p);
+    g_ipc.clear();
+    return AQS_OK;
+}
+
+int aqs_peer_bitswap(aqs_state_t s, void* const* members, int k, const int* local_bits, uint32_t my_value) {
+    REQUIRE_INIT();
+    REQUIRE(s && members && local_bits, "null argument");
+    REQUIRE(k >= 1 && k <= kPeerMaxK, "1 to 3 (global, local) bit pairs per remap");
+    REQUIRE(my_value < (1u << k), "member value out of range");
+    REQUIRE(s->n >= k + 2, "shard too small for a peer remap");
+    PeerSwapArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.mine = s->d;
+    A.k = (uint32_t)k;
+    A.my = my_value;
+    uint64_t fixedmask = 1ull;                               // bit 0: work items are 128-bit vectors
+    for (int i = 0; i < k; ++i) {
+        REQUIRE(local_bits[i] >= 1 && local_bits[i] < s->n, "local bit out of range (bit 0 cannot be remapped)");
+        REQUIRE(!(fixedmask >> local_bits[i] & 1ull), "duplicate local bit");
+        fixedmask |= 1ull << local_bits[i];
+    }
+    int hbit = -1;
+    for (int b = s->n - 1; b >= 1; --b)
+        if (!(fixedmask >> b & 1ull)) { hbit = b; break; }
+    REQUIRE(hbit >= 1, "no free local bit to split the work");
+    A.hbit = (uint32_t)hbit;
+    fixedmask |= 1ull << hbit;
+    bitlist_from_mask(fixedmask, A.fixed);
+    for (uint32_t v = 0; v < (1u << k); ++v) {
+        uint64_t off = 0;
+        for (int i = 0; i < k; ++i)
+            if (v >> i & 1u) off |= 1ull << local_bits[i];
+        A.voff[v] = off;
+        A.peer[v] = (float2*)members[v];
+        REQUIRE(v == my_value || members[v] != nullptr, "null member pointer");
+    }
+    A.n_items = s->N >> A.fixed.n;
+    const uint64_t per_block = (uint64_t)kPeerThreads * kPeerItems;
+    const uint64_t gx = (A.n_items + per_block - 1) / per_block;
+    REQUIRE(gx <= 0x7fffffffull, "grid too large");
+    dim3 grid((unsigned)gx, (1u << k) - 1u);
+    k_peer_bitswap<<<grid, kPeerThreads, 0, s->stream>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return AQS_OK;
 }
 
 // ---- timers -------------------------------------------------------------------------

@@ -56,6 +56,7 @@ ABI_SYMBOLS = [
     "aqs_norm2", "aqs_scale", "aqs_prob_fixed", "aqs_qubit_prob1", "aqs_probabilities", "aqs_collapse_qubit",
     "aqs_sample", "aqs_sample_fixed", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
+    "aqs_state_ipc_export", "aqs_ipc_open", "aqs_ipc_close_all", "aqs_peer_bitswap",
 ]
 
 
@@ -89,6 +90,8 @@ def load():
         "aqs_timer_create": [P(vp)], "aqs_timer_start": [vp, vp], "aqs_timer_stop": [vp, vp],
         "aqs_timer_elapsed_ms": [vp, P(ctypes.c_double)], "aqs_timer_destroy": [vp],
         "aqs_counters_get": [P(Counters)], "aqs_counters_reset": [],
+        "aqs_state_ipc_export": [vp, vp], "aqs_ipc_open": [vp, P(vp)], "aqs_ipc_close_all": [],
+        "aqs_peer_bitswap": [vp, P(vp), i32, P(i32), ctypes.c_uint32],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -98,6 +101,16 @@ def load():
     L.aqs_engine_abi_version.restype = i32
     _lib = L
     return L
+
+
+IPC_HANDLE_BYTES = 64
+
+
+def ipc_open(handle: bytes) -> int:
+    """Map another process's exported state into this one; returns the device pointer (cached by the engine)."""
+    p = ctypes.c_void_p()
+    _check(load().aqs_ipc_open(handle, ctypes.byref(p)))
+    return p.value
 
 
 def _check(rc: int) -> None:
@@ -296,6 +309,21 @@ class State:
 
     def sync(self):
         _check(load().aqs_sync(self._h))
+
+    # -- peer memory (sharded states) -----------------------------------------
+    def ipc_export(self) -> bytes:
+        """CUDA IPC handle of this engine-allocated state (64 bytes) for the other ranks of the node."""
+        buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(load().aqs_state_ipc_export(self._h, buf))
+        return buf.raw
+
+    def peer_bitswap(self, members: Sequence[int], local_bits: Sequence[int], my_value: int):
+        """Swap k (rank bit, local index bit) pairs in place over peer memory (aqs_peer_bitswap).
+        members[v] = device pointer of the group member whose selected rank bits read v."""
+        k = len(local_bits)
+        arr = (ctypes.c_void_p * (1 << k))(*[ctypes.c_void_p(int(p)) if p else None for p in members])
+        lb = (ctypes.c_int * k)(*[int(b) for b in local_bits])
+        _check(load().aqs_peer_bitswap(self._h, arr, k, lb, my_value))
 
     # -- gates ----------------------------------------------------------------
     def apply_ops(self, ops: np.ndarray):

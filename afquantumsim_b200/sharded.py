@@ -25,6 +25,7 @@ north-star extension, with a 64-bit index API beside the 30-qubit drop-in one.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -62,10 +63,97 @@ class _Op:
             self.nd, self.dg = {self.t}, cq
 
 
+class ShardedPlan:
+    """A circuit compiled for one entry layout of a ShardedState: fused local plans interleaved with
+    global-qubit remaps (the sharded counterpart of QCircuit::compile, src/quantum.cpp:199-210).
+    steps: ("plan", eng.Plan, n_ops) | ("p2p", rank_bits, local_bits) | ("nccl", rank_bit)."""
+    __slots__ = ("steps", "entry_pos", "exit_pos", "n_exchanges", "exchange_bytes", "n_local_ops", "n_passes")
+
+    def __init__(self, steps, entry_pos, exit_pos):
+        self.steps, self.entry_pos, self.exit_pos = steps, list(entry_pos), list(exit_pos)
+        self.n_exchanges = self.exchange_bytes = self.n_local_ops = self.n_passes = 0
+
+
+class _CudaMem:
+    """__cuda_array_interface__ view of engine-owned device memory (lets torch / NCCL address a shard)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class _Sched:
+    """Layout bookkeeping while a schedule is emitted: local op records pile up in `pending` until a remap
+    (or the end) turns them into one fused plan."""
+
+    def __init__(self, st: "ShardedState"):
+        self.st = st
+        self.pos = list(st.pos)
+        self.steps: list = []
+        self.pending: List[np.ndarray] = []
+        self.entry = list(st.pos)
+
+    def qubit_at(self, p: int) -> int:
+        return self.pos.index(p)
+
+    def flush(self):
+        if self.pending:
+            st = self.st
+            ops = np.concatenate(self.pending)
+            self.steps.append(("plan", eng.Plan(st.n_local, ops, eng.PLAN_FUSE if st.fuse else 0), len(ops)))
+            self.pending = []
+
+    def local_swap(self, pa: int, pb: int):
+        """exchange the logical qubits at local index bits pa and pb (a SWAP folded into the pending batch)"""
+        if pa == pb:
+            return
+        st = self.st
+        self.pending.append(eng.op_record(eng.OP_SWAP, st._local_qubit(pa), target2=st._local_qubit(pb)))
+        qa, qb = self.qubit_at(pa), self.qubit_at(pb)
+        self.pos[qa], self.pos[qb] = pb, pa
+        st.stats["local_swaps"] += 1
+
+    def exchange(self, pairs):
+        """pairs: [(q_global, q_local)] logical qubits to trade places, all at once where peer memory allows"""
+        st = self.st
+        k = len(pairs)
+        lbits = [self.pos[ql] for _, ql in pairs]
+        if st.p2p and st.n_local >= k + 2 and all(b >= 1 for b in lbits):
+            self.flush()
+            self.steps.append(("p2p", [self.pos[qg] - st.n_local for qg, _ in pairs], lbits))
+            for qg, ql in pairs:
+                self.pos[qg], self.pos[ql] = self.pos[ql], self.pos[qg]
+            return
+        top = st.n_local - 1
+        for qg, ql in pairs:
+            self.local_swap(self.pos[ql], top)      # the half that leaves is then one contiguous block
+            self.flush()
+            pg = self.pos[qg]
+            self.steps.append(("nccl", pg - st.n_local))
+            self.pos[qg], self.pos[ql] = top, pg
+
+    def finish(self) -> ShardedPlan:
+        self.flush()
+        plan = ShardedPlan(self.steps, self.entry, self.pos)
+        shard_bytes = 8 << self.st.n_local
+        for step in self.steps:
+            if step[0] == "plan":
+                plan.n_local_ops += step[2]
+                plan.n_passes += int(step[1].info()["n_launches"])
+            elif step[0] == "p2p":
+                k = len(step[1])
+                plan.n_exchanges += 1
+                plan.exchange_bytes += shard_bytes * ((1 << k) - 1) // (1 << (k + 1))
+            else:
+                plan.n_exchanges += 1
+                plan.exchange_bytes += shard_bytes // 2
+        return plan
+
+
 class ShardedState:
     """A 2^n complex64 state vector sharded over the ranks of a torch.distributed group."""
 
-    def __init__(self, n_qubits: int, device: Optional[torch.device] = None, group=None, fuse: bool = True):
+    def __init__(self, n_qubits: int, device: Optional[torch.device] = None, group=None, fuse: bool = True,
+                 p2p: Optional[bool] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -78,15 +166,50 @@ class ShardedState:
             raise ValueError("each shard needs at least 2 local qubits")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.fuse = fuse
-        self.buf = torch.zeros(1 << self.n_local, dtype=torch.complex64, device=self.device)
-        self.stage = torch.empty(1 << (self.n_local - 1), dtype=torch.complex64, device=self.device)
-        if self.rank == 0:
-            self.buf[0] = 1.0
-        self.state = eng.State.wrap(self.n_local, self.buf.data_ptr())
-        if self.device.type == "cuda":
-            self.state.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
-        self.pos: List[int] = [self.n - 1 - q for q in range(self.n)]   # logical qubit -> index bit
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_plans": 0, "local_ops": 0, "local_swaps": 0}
+        self.stage = None           # half-shard staging buffer of the NCCL path, made on first use
+        self.p2p = False
+        self.peer_ptrs: List[int] = []
+        if p2p is None:
+            p2p = os.environ.get("AQS_SHARD_P2P", "1") != "0"
+        if self.device.type == "cuda":
+            # engine-owned shard (the base of a cudaMalloc allocation, so that it can be exported over CUDA IPC);
+            # torch sees it through __cuda_array_interface__
+            self.state = eng.State(self.n_local)
+            self._mem = _CudaMem(self.state.device_ptr(), 2 << self.n_local)
+            self.buf = torch.view_as_complex(torch.as_tensor(self._mem, device=self.device).view(-1, 2))
+            self.state.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            if p2p and self.world > 1:
+                self._open_peers()
+        else:
+            self.buf = torch.zeros(1 << self.n_local, dtype=torch.complex64, device=self.device)
+            self.state = eng.State.wrap(self.n_local, self.buf.data_ptr())
+        self.pos: List[int] = [self.n - 1 - q for q in range(self.n)]   # logical qubit -> index bit
+        self.set_basis(0)
+
+    def _open_peers(self):
+        """Exchange CUDA IPC handles of the shards; peer memory is used only if EVERY rank mapped every shard."""
+        ok = 1
+        ptrs: List[int] = []
+        try:
+            handle = self.state.ipc_export()
+        except eng.EngineError:
+            handle, ok = bytes(eng.IPC_HANDLE_BYTES), 0
+        t = torch.zeros(self.world, eng.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+        t[self.rank] = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(self.device)
+        dist.all_reduce(t, group=self.group)
+        handles = t.cpu().numpy()
+        if ok:
+            try:
+                for r in range(self.world):
+                    ptrs.append(self.state.device_ptr() if r == self.rank else eng.ipc_open(handles[r].tobytes()))
+            except eng.EngineError:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.p2p = bool(int(flag.item()))
+        self.peer_ptrs = ptrs if self.p2p else []
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------ helpers
     def _qubit_at(self, p: int) -> int:
@@ -99,21 +222,11 @@ class ShardedState:
         """engine (API-style) qubit number of local index bit p"""
         return self.n_local - 1 - p
 
-    def _run_local(self, recs: List[np.ndarray]):
-        if not recs:
-            return
-        ops = np.concatenate(recs)
-        plan = eng.Plan(self.n_local, ops, eng.PLAN_FUSE if self.fuse else 0)
-        self.state.run(plan)
-        self.state.sync()          # the plan's descriptors are freed with `plan`
-        self.stats["local_plans"] += 1
-        self.stats["local_ops"] += len(ops)
-
-    def _translate(self, op: _Op) -> List[np.ndarray]:
-        """One logical op -> local engine ops for THIS rank under the current layout."""
+    def _translate(self, op: _Op, pos: Sequence[int]) -> List[np.ndarray]:
+        """One logical op -> local engine ops for THIS rank under the layout `pos`."""
         ctrl_local, cval = [], 0
         for q, v in op.ctrl:
-            p = self.pos[q]
+            p = pos[q]
             if p >= self.n_local:
                 if self._rank_bit(p) != v:
                     return []                      # control not satisfied on this rank
@@ -122,7 +235,7 @@ class ShardedState:
                 ctrl_local.append(lq)
                 cval |= v << lq
         if op.kind == eng.OP_DIAG:
-            p = self.pos[op.t]
+            p = pos[op.t]
             if p >= self.n_local:
                 f = op.m[3] if self._rank_bit(p) else op.m[0]
                 if f == 1:
@@ -131,29 +244,37 @@ class ShardedState:
                 return [eng.op_record(eng.OP_DIAG, free, [f, 0, 0, f], ctrl_local, ctrl_value=cval)]
             return [eng.op_record(eng.OP_DIAG, self._local_qubit(p), op.m, ctrl_local, ctrl_value=cval)]
         if op.kind == eng.OP_SWAP:
-            return [eng.op_record(eng.OP_SWAP, self._local_qubit(self.pos[op.t]), controls=ctrl_local,
-                                  target2=self._local_qubit(self.pos[op.t2]), ctrl_value=cval)]
-        return [eng.op_record(op.kind, self._local_qubit(self.pos[op.t]), op.m, ctrl_local, ctrl_value=cval)]
+            return [eng.op_record(eng.OP_SWAP, self._local_qubit(pos[op.t]), controls=ctrl_local,
+                                  target2=self._local_qubit(pos[op.t2]), ctrl_value=cval)]
+        return [eng.op_record(op.kind, self._local_qubit(pos[op.t]), op.m, ctrl_local, ctrl_value=cval)]
 
-    # ------------------------------------------------------------------ exchanges
-    def _local_swap_to_top(self, p: int):
-        top = self.n_local - 1
-        if p == top:
-            return
-        self._run_local([eng.op_record(eng.OP_SWAP, self._local_qubit(p), target2=self._local_qubit(top))])
-        qa, qb = self._qubit_at(p), self._qubit_at(top)
-        self.pos[qa], self.pos[qb] = top, p
-        self.stats["local_swaps"] += 1
+    # ------------------------------------------------------------------ remaps
+    def _stream_barrier(self):
+        """Cross-rank barrier ORDERED ON THE STREAM (no host synchronisation): a one-element all_reduce."""
+        dist.all_reduce(self._flag, group=self.group)
 
-    def _exchange(self, q_global: int, q_local: int):
-        """Swap logical qubits q_global (on a rank bit) and q_local (on a local bit)."""
-        pg = self.pos[q_global]
-        assert pg >= self.n_local > self.pos[q_local]
-        self._local_swap_to_top(self.pos[q_local])
-        b = self._rank_bit(pg)
-        peer = self.rank ^ (1 << (pg - self.n_local))
+    def _p2p_swap(self, rank_bits: Sequence[int], local_bits: Sequence[int]):
+        """Trade k rank bits with k local index bits in place over NVLink peer memory (aqs_peer_bitswap)."""
+        k = len(rank_bits)
+        my = sum(((self.rank >> j) & 1) << i for i, j in enumerate(rank_bits))
+        members = []
+        for v in range(1 << k):
+            r = self.rank
+            for i, j in enumerate(rank_bits):
+                r = (r & ~(1 << j)) | (((v >> i) & 1) << j)
+            members.append(self.peer_ptrs[r])
+        self._stream_barrier()      # every member has finished the kernels that precede the remap
+        self.state.peer_bitswap(members, local_bits, my)
+        self._stream_barrier()      # nobody touches its shard while a partner still writes into it
+
+    def _nccl_half_exchange(self, rank_bit: int):
+        """Trade rank bit `rank_bit` with the TOP local bit: half a shard each way with send/recv."""
+        b = (self.rank >> rank_bit) & 1
+        peer = self.rank ^ (1 << rank_bit)
         halves = self.buf.view(2, -1)
         out_half = halves[1 - b]                 # the half whose top local bit differs from my rank bit
+        if self.stage is None:
+            self.stage = torch.empty(1 << (self.n_local - 1), dtype=torch.complex64, device=self.device)
         if self.device.type == "cuda":
             reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, out_half, peer, self.group),
                                            dist.P2POp(dist.irecv, self.stage, peer, self.group)])
@@ -166,36 +287,35 @@ class ShardedState:
                 tmp = out_half.clone()
                 dist.recv(self.stage, peer, self.group); dist.send(tmp, peer, self.group)
         out_half.copy_(self.stage)
-        self.pos[q_global], self.pos[q_local] = self.n_local - 1, pg
-        self.stats["exchanges"] += 1
-        self.stats["exchange_bytes"] += out_half.numel() * 8
 
-    def _next_use(self, q: int, ops: Sequence[_Op]) -> int:
+    @staticmethod
+    def _next_use(q: int, ops: Sequence[_Op]) -> int:
         for i, op in enumerate(ops):
             if q in op.nd:
                 return i
         return 1 << 30
 
     # ------------------------------------------------------------------ gates
-    def apply_ops(self, records: np.ndarray):
-        """Apply primitive ops (struct aqs_op records over all n qubits, API numbering)."""
+    def compile(self, records: np.ndarray) -> ShardedPlan:
+        """Schedule primitive ops (struct aqs_op records over all n qubits, API numbering) for the CURRENT
+        layout: everything executable between two remaps becomes one fused local plan."""
+        sch = _Sched(self)
+        pos = sch.pos
         remaining = [_Op(r) for r in np.ascontiguousarray(records, dtype=eng.OP_DTYPE)]
         while remaining:
             batch, rest = [], []
             blocked_nd, blocked_d = set(), set()
             for op in remaining:
                 conflict = (op.nd & (blocked_nd | blocked_d)) or (op.dg & blocked_nd)
-                local = all(self.pos[q] < self.n_local for q in op.nd)
+                local = all(pos[q] < self.n_local for q in op.nd)
                 if not conflict and local:
                     batch.append(op)
                 else:
                     blocked_nd |= op.nd
                     blocked_d |= op.dg
                     rest.append(op)
-            recs: List[np.ndarray] = []
             for op in batch:
-                recs += self._translate(op)
-            self._run_local(recs)
+                sch.pending += self._translate(op, pos)
             remaining = rest
             if not remaining:
                 break
@@ -203,17 +323,47 @@ class ShardedState:
             wanted: List[int] = []
             for op in remaining:
                 for q in sorted(op.nd):
-                    if self.pos[q] >= self.n_local and q not in wanted:
+                    if pos[q] >= self.n_local and q not in wanted:
                         wanted.append(q)
                 if len(wanted) >= self.g:
                     break
             protect = set()
             for op in remaining[:1]:
                 protect |= op.nd
+            pairs, victims = [], set()
             for qg in wanted[: self.g]:
-                locals_ = [q for q in range(self.n) if self.pos[q] < self.n_local and q not in protect and q not in wanted]
-                victim = max(locals_, key=lambda q: (self._next_use(q, remaining), self.pos[q]))
-                self._exchange(qg, victim)
+                locals_ = [q for q in range(self.n) if pos[q] < self.n_local and q not in protect and q not in wanted
+                           and q not in victims]
+                if self.p2p:
+                    # peer-memory remaps move runs of 2^bit amplitudes: keep them long when there is a choice
+                    high = [q for q in locals_ if pos[q] >= 6]
+                    locals_ = high or [q for q in locals_ if pos[q] >= 1] or locals_
+                victim = max(locals_, key=lambda q: (self._next_use(q, remaining), pos[q]))
+                victims.add(victim)
+                pairs.append((qg, victim))
+            sch.exchange(pairs)
+        return sch.finish()
+
+    def run(self, plan: ShardedPlan) -> None:
+        """Execute a plan compiled for the current layout (asynchronous on the stream)."""
+        if self.pos != plan.entry_pos:
+            raise ValueError("the plan was compiled for a different qubit layout; compile() again")
+        for step in plan.steps:
+            if step[0] == "plan":
+                self.state.run(step[1])
+                self.stats["local_plans"] += 1
+                self.stats["local_ops"] += step[2]
+            elif step[0] == "p2p":
+                self._p2p_swap(step[1], step[2])
+            else:
+                self._nccl_half_exchange(step[1])
+        self.pos = list(plan.exit_pos)
+        self.stats["exchanges"] += plan.n_exchanges
+        self.stats["exchange_bytes"] += plan.exchange_bytes
+
+    def apply_ops(self, records: np.ndarray):
+        """Apply primitive ops: compile for the current layout, then run."""
+        self.run(self.compile(records))
 
     def run_circuit(self, qc) -> None:
         """simulate() for an afquantumsim_b200.aqs.QCircuit on more qubits than one GPU holds."""
@@ -223,25 +373,26 @@ class ShardedState:
     def canonicalize(self):
         """Bring every logical qubit q back to index bit n-1-q."""
         home = lambda q: self.n - 1 - q
+        if all(self.pos[q] == home(q) for q in range(self.n)):
+            return
+        sch = _Sched(self)
+        pos = sch.pos
         # 1. global positions
         for pg in range(self.n - 1, self.n_local - 1, -1):
             q_home = self.n - 1 - pg
-            if self.pos[q_home] == pg:
+            if pos[q_home] == pg:
                 continue
-            if self.pos[q_home] >= self.n_local:      # sits on another rank bit: bring it local first
-                locals_ = [q for q in range(self.n) if self.pos[q] < self.n_local]
-                self._exchange(q_home, locals_[0])
-            self._exchange(self._qubit_at(pg), q_home)
-        # 2. local permutation
+            if pos[q_home] >= self.n_local:      # sits on another rank bit: bring it local first
+                locals_ = [q for q in range(self.n) if pos[q] < self.n_local]
+                sch.exchange([(q_home, max(locals_, key=lambda q: pos[q]))])
+            sch.exchange([(sch.qubit_at(pg), q_home)])
+        # 2. local permutation (SWAPs, fused into one plan)
         for p in range(self.n_local):
             q_home = self.n - 1 - p
-            if self.pos[q_home] != p:
-                other = self._qubit_at(p)
-                self._run_local([eng.op_record(eng.OP_SWAP, self._local_qubit(self.pos[q_home]),
-                                               target2=self._local_qubit(p))])
-                self.pos[other], self.pos[q_home] = self.pos[q_home], p
-                self.stats["local_swaps"] += 1
-        assert all(self.pos[q] == home(q) for q in range(self.n))
+            if pos[q_home] != p:
+                sch.local_swap(pos[q_home], p)
+        assert all(pos[q] == home(q) for q in range(self.n))
+        self.run(sch.finish())
 
     # ------------------------------------------------------------------ measurement
     def _allreduce_i64(self, value: int) -> int:

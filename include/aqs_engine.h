@@ -183,6 +183,23 @@ int aqs_sample_fixed(aqs_state_t s, const uint64_t* u_fixed_host, uint64_t n_dra
  * (std::vector<uint32_t>(2^n), src/quantum.cpp:470,498); hist_host has 2^n entries */
 int aqs_sample_hist(aqs_state_t s, const float* u_host, uint64_t n_draws, uint32_t* hist_host);
 
+/* ---- peer memory: sharded states on one NVLink / NVSwitch node -------------------
+ * No reference counterpart (the reference is single-device).  A state of
+ * n qubits is sharded over 2^g GPUs, one process each; the top g index bits are the rank.
+ * aqs_state_ipc_export / aqs_ipc_open hand an engine-allocated shard to the other processes
+ * (CUDA IPC; opened mappings are cached until aqs_ipc_close_all / aqs_engine_shutdown).
+ * aqs_peer_bitswap swaps k (global bit, local bit) pairs of the sharded index IN PLACE, reading
+ * and writing the partners' shards directly over NVLink: members[v] is the shard of the group
+ * member whose k selected rank bits read v (members[my_value] is ignored), local_bits[i] is the
+ * INDEX-BIT position (not an API qubit number; >= 1) traded with selected rank bit i.  Every
+ * member of the group must call it with the same k and local_bits, between two cross-rank
+ * barriers on the stream (afquantumsim_b200/sharded.py: stream-ordered NCCL all_reduce). */
+#define AQS_IPC_HANDLE_BYTES 64
+int aqs_state_ipc_export(aqs_state_t s, void* handle_out /* AQS_IPC_HANDLE_BYTES */);
+int aqs_ipc_open(const void* handle, void** peer_ptr);
+int aqs_ipc_close_all(void);
+int aqs_peer_bitswap(aqs_state_t s, void* const* members, int k, const int* local_bits, uint32_t my_value);
+
 /* ---- timing (CUDA events on the state's stream) ---------------------------- */
 int aqs_timer_create(aqs_timer_t* out);
 int aqs_timer_start(aqs_timer_t t, aqs_state_t s);

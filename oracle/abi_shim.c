@@ -193,6 +193,29 @@ int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     free(idx); return AQS_OK;
 }
 
+/* peer memory: there is none across CPU processes.  In-process "members" (plain host pointers)
+ * are supported so that tests can check the remap's index arithmetic against a numpy restatement:
+ * member `my` performs every swap it shares with a member of higher value. */
+int aqs_state_ipc_export(aqs_state_t s, void* h) { (void)s; (void)h; return fail(AQS_ERR_STATE, "no peer memory on the cpu shim"); }
+int aqs_ipc_open(const void* h, void** p) { (void)h; (void)p; return fail(AQS_ERR_STATE, "no peer memory on the cpu shim"); }
+int aqs_ipc_close_all(void) { return AQS_OK; }
+int aqs_peer_bitswap(aqs_state_t s, void* const* members, int k, const int* local_bits, uint32_t my) {
+    REQ(s && members && local_bits, "null argument");
+    REQ(k >= 1 && k <= 3 && my < (1u << k), "bad remap");
+    uint64_t sel = 0;
+    for (int i = 0; i < k; ++i) { REQ(local_bits[i] >= 1 && local_bits[i] < s->n, "local bit out of range"); sel |= 1ULL << local_bits[i]; }
+    for (uint64_t x = 0; x < s->N; ++x) {
+        uint32_t v = 0;
+        for (int i = 0; i < k; ++i) v |= (uint32_t)((x >> local_bits[i]) & 1ULL) << i;
+        if (v <= my) continue;
+        uint64_t y = x & ~sel;
+        for (int i = 0; i < k; ++i) y |= (uint64_t)((my >> i) & 1u) << local_bits[i];
+        c32* other = (c32*)members[v];
+        c32 t = s->a[x]; s->a[x] = other[y]; other[y] = t;
+    }
+    return AQS_OK;
+}
+
 int aqs_timer_create(aqs_timer_t* out) { REQ(out, "null"); *out = (aqs_timer_t)calloc(1, sizeof **out); return AQS_OK; }
 int aqs_timer_start(aqs_timer_t t, aqs_state_t s) { (void)s; clock_gettime(CLOCK_MONOTONIC, &t->a); return AQS_OK; }
 int aqs_timer_stop(aqs_timer_t t, aqs_state_t s) { (void)s; clock_gettime(CLOCK_MONOTONIC, &t->b); return AQS_OK; }

@@ -66,19 +66,35 @@ def worker(rank, world, backend, port):
     from tests.lowering import lower_array
 
     g = int(np.log2(world))
-    # 1. random circuits touching global qubits every way (target, control, diagonal, swap)
+    # 1. random circuits touching global qubits every way (target, control, diagonal, swap);
+    #    on GPUs both remap back ends: in-place swaps over peer memory and NCCL half-shard send/recv
+    modes = (True, False) if backend == "cuda" else (False,)
     for n, count, seed in ((g + 3, 60, 1), (g + 6, 150, 2), (g + 9, 200, 3), (12, 250, 4)):
         circ = _random_circuit(orc, n, count, seed)
+        want = orc.simulate(orc.new_state(n), circ)
         for fuse in (True, False):
-            st = ShardedState(n, device=device, fuse=fuse)
-            st.apply_ops(lower_array(circ))
-            got = st.gather()
-            want = orc.simulate(orc.new_state(n), circ)
-            err = orc.rel_l2(got, want)
-            assert err < TOL, (n, seed, fuse, err)
-            assert abs(st.norm2() - 1) < 1e-4
-            if world > 1 and n > g + 3:
-                assert st.stats["exchanges"] > 0
+            for p2p in modes:
+                st = ShardedState(n, device=device, fuse=fuse, p2p=p2p)
+                if backend == "cuda" and world > 1:
+                    assert st.p2p == p2p, "peer memory should be available between the GPUs of one node"
+                st.apply_ops(lower_array(circ))
+                got = st.gather()
+                err = orc.rel_l2(got, want)
+                assert err < TOL, (n, seed, fuse, p2p, err)
+                assert abs(st.norm2() - 1) < 1e-4
+                if world > 1 and n > g + 3:
+                    assert st.stats["exchanges"] > 0
+    # a compiled plan is reusable: same entry layout, same result
+    n = 12
+    circ = _random_circuit(orc, n, 200, 5)
+    want = orc.simulate(orc.new_state(n), circ)
+    st = ShardedState(n, device=device)
+    plan = st.compile(lower_array(circ))
+    for _ in range(2):
+        st.set_basis(0)
+        st.run(plan)
+        assert orc.rel_l2(st.gather(), want) < TOL
+        st.set_basis(0)
     # 2. BASELINE circuits: brickwork and QFT (QFT's CPhase ladder needs no exchange beyond the g H gates)
     n = 12
     st = ShardedState(n, device=device)
