@@ -28,6 +28,9 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "engine_internal.h"
 #include "tile_kernel.cuh"
@@ -410,13 +413,17 @@ static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
 // ---- step 2/3: grouping -----------------------------------------------------
 // Greedy "take what fits, skip what commutes": selects indices of `ops` (in order) whose
 // non-diagonal target bits fit in `cap` more bits on top of `base_bits`, at most `max_take` ops.
+// `scoring`: the caller only counts `taken` (tile choice): stop as soon as every allowed bit is blocked —
+// no butterfly can be taken any more — instead of walking the whole window.
 static uint64_t greedy_group(const std::vector<POp>& ops, const std::vector<int>& cand, uint64_t base_bits,
-                             uint64_t allowed_bits, int cap, size_t max_take, std::vector<int>& taken, std::vector<int>& rest) {
+                             uint64_t allowed_bits, int cap, size_t max_take, std::vector<int>& taken, std::vector<int>& rest,
+                             bool scoring = false) {
     uint64_t bits = base_bits, blocked_nd = 0, blocked_d = 0;
     int room = cap;
     taken.clear();
     rest.clear();
     for (int idx : cand) {
+        if (scoring && (allowed_bits & ~(blocked_nd | blocked_d)) == 0) break;
         const POp& c = ops[idx];
         const uint64_t nd = nd_bits(c), dd = d_bits(c);
         const bool conflict = (nd & (blocked_nd | blocked_d)) || (dd & blocked_nd);
@@ -437,8 +444,10 @@ static uint64_t greedy_group(const std::vector<POp>& ops, const std::vector<int>
 
 // Grow a bit set one bit at a time, each time adding the candidate bit that lets a group take
 // the most ops from the head of `cand`.
+// `noise` > 0 perturbs the scores (seeded, reproducible): the planner runs several such variants and
+// keeps the plan with the fewest passes (build_fused).
 static uint64_t choose_bits(const std::vector<POp>& ops, const std::vector<int>& cand, uint64_t base, uint64_t pool_limit,
-                            int count, int n, size_t max_take) {
+                            int count, int n, size_t max_take, uint64_t& lcg, int noise) {
     const size_t kScore = std::min<size_t>(cand.size(), 768);
     std::vector<int> head(cand.begin(), cand.begin() + kScore), t2, r2;
     uint64_t chosen = base, pool = 0;
@@ -449,9 +458,13 @@ static uint64_t choose_bits(const std::vector<POp>& ops, const std::vector<int>&
         size_t best = 0;
         for (int b = 0; b < n; ++b) {
             if (!(pool >> b & 1ull)) continue;
-            greedy_group(ops, head, chosen | (1ull << b), chosen | (1ull << b), 0, max_take, t2, r2);
+            greedy_group(ops, head, chosen | (1ull << b), chosen | (1ull << b), 0, max_take, t2, r2, true);
             size_t gain = 0;
             for (int idx : t2) gain += (nd_bits(ops[idx]) & ~base) ? 4 : 1;
+            if (noise) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                gain = gain * 16 + (size_t)((lcg >> 40) % (uint64_t)(noise * 16));
+            }
             if (best_bit < 0 || gain > best) { best = gain; best_bit = b; }
         }
         if (best_bit < 0) break;
@@ -755,27 +768,18 @@ struct Emitter {
     }
 };
 
-static int build_fused(aqs_plan_s* p) {
-    const int n = p->n;
-    int T = std::min(n, 12);
-    if (const char* e = std::getenv("AQS_TILE_BITS")) {
-        const int t = std::atoi(e);
-        if (t >= kMinTileBits && t <= kMaxTileBits) T = std::min(n, t);
-    }
+// One planning run over the simplified op list.  variant 0 is the plain greedy; variant v > 0 perturbs
+// the tile-choice scores with a seeded generator.  Fills `passes`; returns an aqs_status and, on
+// failure, the message in `err` (the function runs on worker threads: no thread-local error state).
+static int plan_variant(int n, int T, const std::vector<POp>& ops, int variant, std::vector<FusedPass>& passes, std::string& err) {
     const int TB = T - kRegBits;
     const uint64_t all_bits = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     const uint64_t low_mask = (1ull << kLaneBits) - 1ull;
     const size_t kMaxTake = kOpsLarge;         // upper bound only: the emission loop enforces the descriptor budget
-
-    std::vector<POp> ops = simplify(n, p->ops);
-    if (std::getenv("AQS_PLAN_DUMP") && std::atoi(std::getenv("AQS_PLAN_DUMP")) > 2)
-        for (size_t i = 0; i < ops.size(); ++i) {
-            const POp& o = ops[i];
-            std::fprintf(stderr, "  op %zu: bit %d %s cmask %llx mux %d cost %d/%d  m0 = [%.3f%+.3fi %.3f%+.3fi; %.3f%+.3fi %.3f%+.3fi]\n", i, o.p,
-                         o.diag ? "diag" : "mat", (unsigned long long)o.cmask, o.mux, mat_cost(o.m[0]), o.mux >= 0 ? mat_cost(o.m[1]) : -1,
-                         o.m[0][0].real(), o.m[0][0].imag(), o.m[0][1].real(), o.m[0][1].imag(), o.m[0][2].real(), o.m[0][2].imag(),
-                         o.m[0][3].real(), o.m[0][3].imag());
-        }
+    uint64_t lcg = (uint64_t)variant * 0x9E3779B97F4A7C15ull + 1ull;
+    const int noise = variant ? 4 : 0;
+    auto fail = [&](int code, const char* msg) { err = msg; return code; };
+    passes.clear();
     // Sliding window over the op stream: a pass looks at the ops deferred by earlier passes plus
     // the next kWindow ops, so planning is O(passes * window) even for million-op circuits
     // (Grover-26 with 6433 iterations lowers to ~1e6 ops).
@@ -790,7 +794,7 @@ static int build_fused(aqs_plan_s* p) {
         // planning time matters more).
         uint64_t tile;
         if (ops.size() <= 60000) {
-            const uint64_t chosen = choose_bits(ops, cand, low_mask, all_bits, T - kLaneBits, n, kMaxTake);
+            const uint64_t chosen = choose_bits(ops, cand, low_mask, all_bits, T - kLaneBits, n, kMaxTake, lcg, noise);
             tile = greedy_group(ops, cand, chosen, chosen, 0, kMaxTake, taken, rest);
         } else {
             tile = greedy_group(ops, cand, low_mask, all_bits, T - kLaneBits, kMaxTake, taken, rest);
@@ -922,9 +926,55 @@ static int build_fused(aqs_plan_s* p) {
         io_offsets(layouts.back(), fp.st_toff, fp.st_roff);
         fp.scale = make_float2((float)pass_scale.real(), (float)pass_scale.imag());
         fp.has_scale = (pass_scale != cd(1.0, 0.0));
-        p->passes.push_back(std::move(fp));
+        passes.push_back(std::move(fp));
         cand.swap(rest);
     }
+    return AQS_OK;
+}
+
+// The greedy tile choice is sensitive to ties (brickwork: 21 passes at n = 30 but 27 at n = 31).  So
+// the planner runs a few seeded variants of it in parallel host threads and keeps the plan with
+// the fewest passes (then the fewest layouts): 20 passes for both.  Deterministic: the seeds are fixed
+// and the choice does not depend on thread timing, so every rank of a sharded run builds the same plan.
+static int build_fused(aqs_plan_s* p) {
+    const int n = p->n;
+    int T = std::min(n, 12);
+    if (const char* e = std::getenv("AQS_TILE_BITS")) {
+        const int t = std::atoi(e);
+        if (t >= kMinTileBits && t <= kMaxTileBits) T = std::min(n, t);
+    }
+    const std::vector<POp> ops = simplify(n, p->ops);
+    if (std::getenv("AQS_PLAN_DUMP") && std::atoi(std::getenv("AQS_PLAN_DUMP")) > 2)
+        for (size_t i = 0; i < ops.size(); ++i) {
+            const POp& o = ops[i];
+            std::fprintf(stderr, "  op %zu: bit %d %s cmask %llx mux %d cost %d/%d  m0 = [%.3f%+.3fi %.3f%+.3fi; %.3f%+.3fi %.3f%+.3fi]\n", i, o.p,
+                         o.diag ? "diag" : "mat", (unsigned long long)o.cmask, o.mux, mat_cost(o.m[0]), o.mux >= 0 ? mat_cost(o.m[1]) : -1,
+                         o.m[0][0].real(), o.m[0][0].imag(), o.m[0][1].real(), o.m[0][1].imag(), o.m[0][2].real(), o.m[0][2].imag(),
+                         o.m[0][3].real(), o.m[0][3].imag());
+        }
+    int variants = 8;
+    if (const char* e = std::getenv("AQS_PLAN_VARIANTS")) variants = std::max(1, std::min(64, std::atoi(e)));
+    if (ops.size() > 20000 || ops.size() < 64 || n <= T) variants = 1;     // long circuits: planning time matters more
+    std::vector<std::vector<FusedPass>> out(variants);
+    std::vector<std::string> errs(variants);
+    std::vector<int> rcs(variants, AQS_OK);
+    if (variants == 1) {
+        rcs[0] = plan_variant(n, T, ops, 0, out[0], errs[0]);
+    } else {
+        std::vector<std::thread> workers;
+        for (int v = 1; v < variants; ++v)
+            workers.emplace_back([&, v]() { rcs[v] = plan_variant(n, T, ops, v, out[v], errs[v]); });
+        rcs[0] = plan_variant(n, T, ops, 0, out[0], errs[0]);
+        for (auto& w : workers) w.join();
+    }
+    int best = -1;
+    auto layouts = [](const std::vector<FusedPass>& ps) { size_t c = 0; for (auto& fp : ps) c += fp.segs.size(); return c; };
+    for (int v = 0; v < variants; ++v) {
+        if (rcs[v] != AQS_OK) continue;
+        if (best < 0 || out[v].size() < out[best].size() || (out[v].size() == out[best].size() && layouts(out[v]) < layouts(out[best]))) best = v;
+    }
+    if (best < 0) return fail(rcs[0], errs[0]);
+    p->passes = std::move(out[best]);
     return AQS_OK;
 }
 
@@ -981,21 +1031,67 @@ static void fill_params(PassParams& P, float2* state, const FusedPass& fp) {
 static size_t tile_smem_bytes(int T, size_t n_ops) { return (sizeof(float2) << T) + (n_ops + 1) * sizeof(DevOp); }
 
 template <int T>
-static cudaError_t launch_tile(const PassParams& P, const FusedPass& fp, cudaStream_t st) {
-    k_tile2<T><<<(unsigned)fp.n_tiles, 1 << (T - kRegBits), tile_smem_bytes(T, fp.ops.size()), st>>>(P);
+static cudaError_t launch_tile(const PassParams& P, uint64_t n_tiles, size_t n_ops, cudaStream_t st) {
+    k_tile2<T><<<(unsigned)n_tiles, 1 << (T - kRegBits), tile_smem_bytes(T, n_ops), st>>>(P);
     return cudaGetLastError();
 }
 
-static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st) {
+// Which tiles of a pass rank r of 2^g runs when the state is one flat address range over the GPUs
+// (flat.cu).  The top g index bits are the rank.  Rank bits OUTSIDE the tile pin the matching bits of
+// the tile number to the rank's own (those tiles are local); for every rank bit INSIDE the tile — the
+// tile then spans several GPUs — one more non-tile local bit (the highest available) is pinned to the
+// rank's value on it, so that the GPUs sharing a tile group split it evenly.  Always g pinned bits.
+struct ShardCut {
+    uint32_t fix_n = 0, fix_or = 0;
+    uint8_t fix_pos[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int rank_bits_in_tile = 0;
+};
+static int shard_cut(int n, const FusedPass& fp, int rank, int g, ShardCut& cut) {
+    uint64_t tile = 0;
+    for (int j = 0; j < fp.tile.n; ++j) tile |= 1ull << fp.tile.pos[j];
+    int compact_of[64], nb = 0;
+    for (int b = 0; b < n; ++b) compact_of[b] = (tile >> b & 1ull) ? -1 : nb++;
+    uint32_t mask = 0, val = 0;
+    int spare = n - g - 1;                       // next candidate local bit for an in-tile rank bit
+    for (int i = 0; i < g; ++i) {
+        const int b = n - g + i;
+        const uint32_t v = (uint32_t)(rank >> i) & 1u;
+        int where;
+        if (!(tile >> b & 1ull)) {
+            where = compact_of[b];
+        } else {
+            ++cut.rank_bits_in_tile;
+            while (spare >= 0 && ((tile >> spare & 1ull) || (mask >> compact_of[spare] & 1u))) --spare;
+            if (spare < 0) return fail(AQS_ERR_STATE, "no local bit left to split a tile group between its GPUs");
+            where = compact_of[spare--];
+        }
+        mask |= 1u << where;
+        val |= v << where;
+    }
+    cut.fix_or = val;
+    for (int c = 0; c < 32; ++c)
+        if (mask >> c & 1u) cut.fix_pos[cut.fix_n++] = (uint8_t)c;
+    return AQS_OK;
+}
+
+static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, const ShardCut* cut = nullptr) {
     if (fp.n_tiles > 0x7fffffffull) return fail(AQS_ERR_INVALID, "grid too large");
     PassParams P;
     fill_params(P, state, fp);
+    uint64_t n_tiles = fp.n_tiles;
+    if (cut && cut->fix_n) {        // sharded run: 1 / 2^g of the tiles
+        P.fix_n = cut->fix_n;
+        P.fix_or = cut->fix_or;
+        std::memcpy(P.fix_pos, cut->fix_pos, sizeof P.fix_pos);
+        n_tiles >>= cut->fix_n;
+    }
+    const size_t n_ops = fp.ops.size();
     cudaError_t e;
     switch (fp.T) {
-        case 10: e = launch_tile<10>(P, fp, st); break;
-        case 11: e = launch_tile<11>(P, fp, st); break;
-        case 12: e = launch_tile<12>(P, fp, st); break;
-        default: e = launch_tile<13>(P, fp, st); break;
+        case 10: e = launch_tile<10>(P, n_tiles, n_ops, st); break;
+        case 11: e = launch_tile<11>(P, n_tiles, n_ops, st); break;
+        case 12: e = launch_tile<12>(P, n_tiles, n_ops, st); break;
+        default: e = launch_tile<13>(P, n_tiles, n_ops, st); break;
     }
     if (e != cudaSuccess) return fail_cuda(e, "tile kernel launch", __LINE__);
     count_launch(1);
@@ -1135,6 +1231,43 @@ int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
     count_ops(p->ops.size());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "plan run", __LINE__);
+    return AQS_OK;
+}
+
+// Sharded run on a flat multi-GPU state (flat.cu): passes [first, first + count) of a fused plan, this
+// rank's share of the tiles only.  The caller separates passes whose tiles span GPUs from their
+// neighbours with cross-rank barriers on the stream (aqs_plan_pass_span tells which ones do).
+int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t first, uint64_t count, int rank, int log2_world) {
+    if (!s || !p) return fail(AQS_ERR_INVALID, "null handle");
+    if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
+    if (p->passes.empty()) return fail(AQS_ERR_INVALID, "sharded runs need a fused plan (AQS_PLAN_FUSE)");
+    if (first + count > p->passes.size()) return fail(AQS_ERR_INVALID, "pass range out of bounds");
+    if (log2_world < 0 || log2_world > 6 || rank < 0 || rank >= (1 << log2_world)) return fail(AQS_ERR_INVALID, "bad rank");
+    if (p->n - p->passes[0].T < log2_world) return fail(AQS_ERR_INVALID, "state too small to shard the tiles of a pass");
+    int up = ensure_uploaded(p);
+    if (up) return up;
+    p->last_stream = s->stream;
+    p->ran = true;
+    for (uint64_t i = first; i < first + count; ++i) {
+        ShardCut cut;
+        int rc = shard_cut(p->n, p->passes[i], rank, log2_world, cut);
+        if (rc) return rc;
+        rc = launch_pass(s->d, p->passes[i], s->stream, &cut);
+        if (rc) return rc;
+    }
+    if (first == 0) count_ops(p->ops.size());
+    return AQS_OK;
+}
+
+// number of rank bits (the top log2_world index bits) inside the tile of fused pass `index`:
+// 0 means every tile of the pass lies in ONE shard
+int aqs_plan_pass_span(aqs_plan_t p, uint64_t index, int log2_world, int* rank_bits_in_tile) {
+    if (!p || !rank_bits_in_tile) return fail(AQS_ERR_INVALID, "null argument");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    int c = 0;
+    const FusedPass& fp = p->passes[index];
+    for (int j = 0; j < fp.tile.n; ++j) c += fp.tile.pos[j] >= p->n - log2_world;
+    *rank_bits_in_tile = c;
     return AQS_OK;
 }
 

@@ -149,6 +149,12 @@ struct alignas(16) PassParams {
     uint64_t st_toff[kMaxThreadBits];
     uint64_t st_roff[kRegBits];
     BitList tile;          // global positions of the tile bits, ascending (tile.pos[0..4] = 0..4)
+    // Sharded runs (aqs_plan_run_shard): this launch covers only the tiles whose number has the bits
+    // fix_pos[0..fix_n) (ascending positions in the compact tile-number space) equal to those of fix_or;
+    // blockIdx.x enumerates the remaining bits.  fix_n = 0: the launch covers every tile.
+    uint32_t fix_n;
+    uint32_t fix_or;
+    uint8_t fix_pos[8];
     TileSeg segs[kMaxSegs];
 };
 static_assert(sizeof(PassParams) <= 4096, "kernel parameter space");
@@ -238,11 +244,11 @@ __device__ __forceinline__ void shear(f2& x, f2& y, const ShearCoef& k) {
 
 // Per-op prelude shared by every body: evaluates the predicate only when the planner flagged one.
 // Returns false when this thread skips the op; `use_b` = take coefficient set b (TF_MUX).
-__device__ __forceinline__ bool op_predicate(const DevOp& op, uint32_t flags, uint32_t tpred, uint32_t tid, bool& use_b) {
+__device__ __forceinline__ bool op_predicate(const DevOp& op, uint32_t flags, uint32_t tpred, uint32_t tid, uint32_t tile_no, bool& use_b) {
     use_b = false;
     if (flags & TF_PRED) {
         const uint2 blk = *reinterpret_cast<const uint2*>(&op.b_mask);
-        const bool ok = ((blockIdx.x & blk.x) == blk.y) && ((tid & (tpred & 0xffffu)) == (tpred >> 16));
+        const bool ok = ((tile_no & blk.x) == blk.y) && ((tid & (tpred & 0xffffu)) == (tpred >> 16));
         if (!ok) {
             if (!(flags & TF_MUX)) return false;
             use_b = true;
@@ -348,7 +354,7 @@ __device__ __forceinline__ ShearCoef make_coef(bool shi_py, float a, float b, fl
     k.sy = im ? 0.f : sy; k.qy = im ? sy : 0.f;
     return k;
 }
-__device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint32_t tid, ShearCoef& ka, ShearCoef& kb) {
+__device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint32_t tid, uint32_t tile_no, ShearCoef& ka, ShearCoef& kb) {
     const uint32_t flags = hd.h.x >> 16;
     const bool py = (flags & TF_PY) != 0;
     const bool shi_py = py && (((hd.h.x >> 3) & 0x1fu) >= 15u);
@@ -359,7 +365,7 @@ __device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint3
         const float4 cb = *reinterpret_cast<const float4*>(&op.b[0]);
         const ShearCoef kset_b = make_coef(shi_py, cb.x, cb.y, cb.z, cb.w, py ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0);
         bool use_b;
-        run = op_predicate(op, flags, hd.h.z, tid, use_b);
+        run = op_predicate(op, flags, hd.h.z, tid, tile_no, use_b);
         if (use_b) ka = kset_b;
         kb = ka;
         if (flags & TF_REGMUX) kb = kset_b;
@@ -393,7 +399,14 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
     const DevOp* sops = reinterpret_cast<const DevOp*>(sm + (1u << T));
 
     const uint32_t tid = threadIdx.x;
-    const uint64_t gbase = deposit_zeros((uint64_t)blockIdx.x, P.tile);
+    // tile number: blockIdx.x, with the bits this rank holds fixed inserted (sharded runs)
+    uint32_t tile_no = blockIdx.x;
+    for (uint32_t i = 0; i < P.fix_n; ++i) {
+        const uint32_t p = P.fix_pos[i];
+        tile_no = ((tile_no >> p) << (p + 1)) | (tile_no & ((1u << p) - 1u));
+    }
+    tile_no |= P.fix_or;
+    const uint64_t gbase = deposit_zeros((uint64_t)tile_no, P.tile);
     {
         // descriptors -> shared memory (16 bytes per thread per step; the list ends with a sentinel)
         const uint4* src = reinterpret_cast<const uint4*>(P.ops);
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
             if (grp < 20u) {
                 // shears: grp = kind * 5 + tk (+ 10 with a prescale)
                 ShearCoef ka, kb;
-                if (!shear_prelude(op, hd, tid, ka, kb)) continue;
+                if (!shear_prelude(op, hd, tid, tile_no, ka, kb)) continue;
                 if (grp < 10u) {
                     if (grp < 5u) AQS_SH5(TK_SHR, false, grp);
                     else AQS_SH5(TK_SHI, false, grp - 5u);
@@ -504,7 +517,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
                 }
             } else {
                 bool use_b;
-                const bool run = op_predicate(op, word >> 16, hd.h.z, tid, use_b);
+                const bool run = op_predicate(op, word >> 16, hd.h.z, tid, tile_no, use_b);
                 const uint32_t mask = hd.h.y;
                 const float4 c0 = hd.a;
                 if (grp >= 23u) {

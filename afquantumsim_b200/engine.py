@@ -57,6 +57,7 @@ ABI_SYMBOLS = [
     "aqs_sample", "aqs_sample_fixed", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
     "aqs_state_ipc_export", "aqs_ipc_open", "aqs_ipc_close_all", "aqs_peer_bitswap",
+    "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span",
 ]
 
 
@@ -92,6 +93,9 @@ def load():
         "aqs_counters_get": [P(Counters)], "aqs_counters_reset": [],
         "aqs_state_ipc_export": [vp, vp], "aqs_ipc_open": [vp, P(vp)], "aqs_ipc_close_all": [],
         "aqs_peer_bitswap": [vp, P(vp), i32, P(i32), ctypes.c_uint32],
+        "aqs_flat_create": [u64, i32, i32, P(vp), P(i32)], "aqs_flat_attach": [vp, i32, i32],
+        "aqs_flat_ptr": [vp, P(vp), P(vp)], "aqs_flat_destroy": [vp],
+        "aqs_plan_run_shard": [vp, vp, u64, u64, i32, i32], "aqs_plan_pass_span": [vp, u64, i32, P(i32)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -176,6 +180,36 @@ def op_record(kind: int, target: int, m: Sequence[complex] = (1, 0, 0, 1), contr
     return r
 
 
+class FlatSpace:
+    """aqs_flat_t: the shards of every GPU of the node mapped back to back into one virtual address range."""
+
+    def __init__(self, shard_bytes: int, world: int, rank: int):
+        ensure_init()
+        self._h = ctypes.c_void_p()
+        fd = ctypes.c_int(-1)
+        _check(load().aqs_flat_create(shard_bytes, world, rank, ctypes.byref(self._h), ctypes.byref(fd)))
+        self.fd = fd.value          # POSIX handle of this rank's shard, to be passed to the other processes
+
+    def attach(self, peer_rank: int, fd: int):
+        _check(load().aqs_flat_attach(self._h, peer_rank, fd))
+
+    def pointers(self):
+        base, own = ctypes.c_void_p(), ctypes.c_void_p()
+        _check(load().aqs_flat_ptr(self._h, ctypes.byref(base), ctypes.byref(own)))
+        return base.value, own.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().aqs_flat_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Plan:
     """aqs_plan_t: a compiled op list (QCircuit::compile, src/quantum.cpp:199-210)."""
 
@@ -190,6 +224,12 @@ class Plan:
         pi = PlanInfo()
         _check(load().aqs_plan_get_info(self._h, ctypes.byref(pi)))
         return {k: getattr(pi, k) for k, _ in PlanInfo._fields_}
+
+    def pass_span(self, index: int, log2_world: int) -> int:
+        """How many rank bits (top log2_world index bits) the tile of fused pass `index` contains."""
+        v = ctypes.c_int()
+        _check(load().aqs_plan_pass_span(self._h, index, log2_world, ctypes.byref(v)))
+        return v.value
 
     def export_pass(self, index: int) -> bytes:
         """Raw launch descriptors of fused pass `index` (tests/tile_emulator.py parses them)."""
@@ -332,6 +372,10 @@ class State:
 
     def run(self, plan: Plan):
         _check(load().aqs_plan_run(self._h, plan._h))
+
+    def run_shard(self, plan: Plan, first: int, count: int, rank: int, log2_world: int):
+        """This rank's share of passes [first, first + count) on a flat multi-GPU state (aqs_plan_run_shard)."""
+        _check(load().aqs_plan_run_shard(self._h, plan._h, first, count, rank, log2_world))
 
     # -- measurement ------------------------------------------------------------
     def norm2(self) -> float:

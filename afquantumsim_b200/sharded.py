@@ -24,6 +24,7 @@ north-star extension, with a 64-bit index API beside the 30-qubit drop-in one.
 """
 from __future__ import annotations
 
+import atexit
 import math
 import os
 from typing import List, Optional, Sequence
@@ -61,6 +62,20 @@ class _Op:
             self.nd, self.dg = {self.t, self.t2}, cq
         else:
             self.nd, self.dg = {self.t}, cq
+
+
+# Flat address spaces are recycled like the engine's state buffers: creating one means an 8 GiB physical
+# allocation, a file-descriptor exchange between the processes and page-table updates for every peer shard,
+# and the API's normal use is a new state per run.  Keyed by geometry; reused only if EVERY rank has one.
+_FLAT_CACHE: dict = {}
+
+
+def _drop_flat_cache():
+    while _FLAT_CACHE:
+        _FLAT_CACHE.popitem()[1].close()
+
+
+atexit.register(_drop_flat_cache)
 
 
 class ShardedPlan:
@@ -153,7 +168,7 @@ class ShardedState:
     """A 2^n complex64 state vector sharded over the ranks of a torch.distributed group."""
 
     def __init__(self, n_qubits: int, device: Optional[torch.device] = None, group=None, fuse: bool = True,
-                 p2p: Optional[bool] = None):
+                 p2p: Optional[bool] = None, flat: Optional[bool] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -170,9 +185,15 @@ class ShardedState:
         self.stage = None           # half-shard staging buffer of the NCCL path, made on first use
         self.p2p = False
         self.peer_ptrs: List[int] = []
+        self.flat = None            # eng.FlatSpace: every shard of the node in one virtual address range
+        self.flat_state = None      # engine handle on the WHOLE 2^n state (fused plans run on it shard by shard)
         if p2p is None:
             p2p = os.environ.get("AQS_SHARD_P2P", "1") != "0"
-        if self.device.type == "cuda":
+        if flat is None:
+            flat = p2p and os.environ.get("AQS_SHARD_FLAT", "1") != "0"
+        if self.device.type == "cuda" and flat and fuse and self.world > 1 and self._open_flat():
+            pass
+        elif self.device.type == "cuda":
             # engine-owned shard (the base of a cudaMalloc allocation, so that it can be exported over CUDA IPC);
             # torch sees it through __cuda_array_interface__
             self.state = eng.State(self.n_local)
@@ -186,6 +207,118 @@ class ShardedState:
             self.state = eng.State.wrap(self.n_local, self.buf.data_ptr())
         self.pos: List[int] = [self.n - 1 - q for q in range(self.n)]   # logical qubit -> index bit
         self.set_basis(0)
+
+    def _open_flat(self) -> bool:
+        """Map the shards of all ranks back to back into one virtual address range (engine: flat.cu).
+        Needs shards that are a multiple of the 2 MiB mapping granularity; all-or-nothing across ranks."""
+        shard_bytes = 8 << self.n_local
+        ok, space, fds = 1, None, {}
+        if shard_bytes % (2 << 20) or self.n_local < 12 + self.g:
+            return False            # the same answer on every rank: no consensus round needed
+
+        def agreed(value: int) -> bool:
+            flag = torch.tensor([value], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            return bool(int(flag.item()))
+
+        self._flat_key = (shard_bytes, self.world, self.rank, id(self.group))
+        space = _FLAT_CACHE.pop(self._flat_key, None)
+        if not agreed(1 if space is not None else 0):
+            if space is not None:
+                space.close()
+            space = None
+            try:
+                space = eng.FlatSpace(shard_bytes, self.world, self.rank)
+            except eng.EngineError:
+                ok = 0
+            if not agreed(ok):
+                if space is not None:
+                    space.close()
+                return False
+            try:
+                fds = self._exchange_fds(space.fd)
+                for r, fd in fds.items():
+                    space.attach(r, fd)
+            except (eng.EngineError, OSError):
+                ok = 0
+            finally:
+                for fd in fds.values():
+                    os.close(fd)
+            if not agreed(ok):
+                space.close()
+                return False
+        base, own = space.pointers()
+        self.flat = space
+        self.flat_state = eng.State.wrap(self.n, base)
+        self.state = eng.State.wrap(self.n_local, own)
+        self._mem = _CudaMem(own, 2 << self.n_local)
+        self.buf = torch.view_as_complex(torch.as_tensor(self._mem, device=self.device).view(-1, 2))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.state.set_stream(stream)
+        self.flat_state.set_stream(stream)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return True
+
+    def close(self):
+        """Give the flat address space back for the next state of the same geometry."""
+        space, self.flat = self.flat, None
+        if space is not None:
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+            self.flat_state = None
+            old = _FLAT_CACHE.pop(self._flat_key, None)
+            if old is not None:
+                old.close()
+            _FLAT_CACHE[self._flat_key] = space
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _exchange_fds(self, fd: int) -> dict:
+        """Hand this rank's shard (a POSIX file descriptor) to every other rank of the node and collect
+        theirs: SCM_RIGHTS over unix-domain sockets."""
+        import socket
+        import threading
+        import uuid
+        token = [uuid.uuid4().hex[:12] if self.rank == 0 else None]
+        dist.broadcast_object_list(token, src=0, group=self.group)
+        path = lambda r: f"/tmp/aqs_flat_{token[0]}_{r}.sock"
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(path(self.rank))
+        srv.listen(self.world)
+        srv.settimeout(120)
+
+        def serve():
+            for _ in range(self.world - 1):
+                conn, _ = srv.accept()
+                socket.send_fds(conn, [b"f"], [fd])
+                conn.close()
+
+        th = threading.Thread(target=serve, daemon=True)
+        th.start()
+        dist.barrier(group=self.group)          # every rank is listening
+        fds = {}
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.settimeout(120)
+                c.connect(path(r))
+                _, got, _, _ = socket.recv_fds(c, 16, 1)
+                c.close()
+                fds[r] = got[0]
+        finally:
+            th.join(timeout=130)
+            srv.close()
+            try:
+                os.unlink(path(self.rank))
+            except OSError:
+                pass
+        return fds
 
     def _open_peers(self):
         """Exchange CUDA IPC handles of the shards; peer memory is used only if EVERY rank mapped every shard."""
@@ -298,7 +431,22 @@ class ShardedState:
     # ------------------------------------------------------------------ gates
     def compile(self, records: np.ndarray) -> ShardedPlan:
         """Schedule primitive ops (struct aqs_op records over all n qubits, API numbering) for the CURRENT
-        layout: everything executable between two remaps becomes one fused local plan."""
+        layout: everything executable between two remaps becomes one fused local plan.  On a flat
+        address space there is nothing to schedule: ONE fused plan over all n qubits, no remaps."""
+        if self.flat_state is not None:
+            recs = np.ascontiguousarray(records, dtype=eng.OP_DTYPE)
+            plan = ShardedPlan([], self.pos, self.pos)
+            if len(recs):
+                ep = eng.Plan(self.n, recs, eng.PLAN_FUSE)
+                n_passes = int(ep.info()["n_fused_passes"])
+                spans = [ep.pass_span(i, self.g) for i in range(n_passes)]
+                plan.steps.append(("flat", ep, spans, len(recs)))
+                plan.n_local_ops, plan.n_passes = len(recs), n_passes
+                # NVLink bytes this rank writes: in a pass whose tile holds j rank bits, (2^j - 1) / 2^j of the
+                # amplitudes it processes (one shard's worth) live on peers
+                plan.n_exchanges = sum(1 for j in spans if j)
+                plan.exchange_bytes = sum((8 << self.n_local) * ((1 << j) - 1) // (1 << j) for j in spans)
+            return plan
         sch = _Sched(self)
         pos = sch.pos
         remaining = [_Op(r) for r in np.ascontiguousarray(records, dtype=eng.OP_DTYPE)]
@@ -355,11 +503,38 @@ class ShardedState:
                 self.stats["local_ops"] += step[2]
             elif step[0] == "p2p":
                 self._p2p_swap(step[1], step[2])
+            elif step[0] == "flat":
+                self._run_flat(step[1], step[2])
+                self.stats["local_plans"] += 1
+                self.stats["local_ops"] += step[3]
             else:
                 self._nccl_half_exchange(step[1])
         self.pos = list(plan.exit_pos)
         self.stats["exchanges"] += plan.n_exchanges
         self.stats["exchange_bytes"] += plan.exchange_bytes
+
+    def _run_flat(self, plan: "eng.Plan", spans: Sequence[int]):
+        """This rank's share of every pass of a whole-state fused plan.  A pass whose tile holds no rank
+        bit touches only this rank's shard; one that does reads and writes peer memory over NVLink, so a
+        stream-ordered barrier separates it from its neighbours (all of it asynchronous on the stream)."""
+        i, n, dirty = 0, len(spans), False
+        while i < n:
+            if spans[i]:
+                self._stream_barrier()
+                self.flat_state.run_shard(plan, i, 1, self.rank, self.g)
+                dirty = True
+                i += 1
+            else:
+                j = i
+                while j < n and not spans[j]:
+                    j += 1
+                if dirty:
+                    self._stream_barrier()
+                    dirty = False
+                self.flat_state.run_shard(plan, i, j - i, self.rank, self.g)
+                i = j
+        if dirty:
+            self._stream_barrier()
 
     def apply_ops(self, records: np.ndarray):
         """Apply primitive ops: compile for the current layout, then run."""

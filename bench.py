@@ -375,6 +375,7 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
     norm2 = st.norm2()
     assert abs(norm2 - 1.0) < 1e-3, f"state norm drifted: {norm2}"
     remap_p2p, plan_passes, plan_local_ops = bool(st.p2p), plan.n_passes, plan.n_local_ops
+    flat_mode = st.flat_state is not None
     del plan
 
     # e2e: host-built gate list -> ops -> sharded simulate -> 1000-draw sample read back, every step
@@ -413,8 +414,11 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
         "config": {
             "workload": (f"brickwork-{n} depth {args.depth}" if args.workload == "brickwork" else f"fourier_transform({n})")
                         + f": {gate_apps} gate applications on ONE 2^{n} state; {S_shard / 2**30:.0f} GiB shard per GPU",
-            "parallelism": f"state sharded over {world} GPUs on the top {g} qubits; global-qubit remaps "
-                           + ("in place over NVLink peer memory (aqs_peer_bitswap)" if remap_p2p else "as half-shard NCCL send/recv"),
+            "parallelism": f"state sharded over {world} GPUs on the top {g} qubits; "
+                           + ("all shards in one flat NVLink address space: one fused plan over the whole state, each GPU runs "
+                              "1/N of the tiles of every pass, tiles that contain rank bits load/store peer memory" if flat_mode
+                              else "global-qubit remaps " + ("in place over NVLink peer memory (aqs_peer_bitswap)" if remap_p2p
+                                                            else "as half-shard NCCL send/recv")),
             "fusion": "on", "l2": "shard is 8 GiB >> 126 MB L2",
         },
         "raw_gate_apps_per_s": gate_apps / (ms * 1e-3),
@@ -424,7 +428,7 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
                 "what": "gate list -> ops -> ShardedState simulate -> 1000-draw distributed sample, host wall clock"},
         "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
         "clocks": clocks,
-        "exchange": {"per_step": exchanges, "bytes_per_rank_per_step": xbytes, "peer_memory": remap_p2p,
+        "exchange": {"per_step": exchanges, "bytes_per_rank_per_step": xbytes, "peer_memory": remap_p2p or flat_mode, "flat_address_space": flat_mode,
                      "local_passes_per_step": plan_passes, "local_ops_per_step": plan_local_ops,
                      "note": "bytes each rank writes to its peers over NVLink per step (it reads as many)"},
         "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,

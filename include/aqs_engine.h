@@ -200,6 +200,26 @@ int aqs_ipc_open(const void* handle, void** peer_ptr);
 int aqs_ipc_close_all(void);
 int aqs_peer_bitswap(aqs_state_t s, void* const* members, int k, const int* local_bits, uint32_t my_value);
 
+/* ---- flat multi-GPU address space ----------------------------------------------
+ * No reference counterpart.  Every rank allocates its shard with the CUDA virtual memory
+ * management API, exports it as a POSIX file descriptor (*fd_out; the host layer passes it to
+ * the other processes, afquantumsim_b200/sharded.py), imports the others' (aqs_flat_attach)
+ * and maps all `world` shards back to back: amplitude k of the whole 2^n state is at
+ * base + 8k on every GPU.  aqs_state_wrap(n, base) then gives a state handle on the WHOLE
+ * state, and aqs_plan_run_shard runs this rank's share (1/world of the tiles) of passes
+ * [first, first + count) of a fused plan on it: a pass whose tile contains rank bits reads and
+ * writes peer memory over NVLink while it computes.  aqs_plan_pass_span reports how many rank
+ * bits a pass's tile contains; the caller puts a cross-rank barrier on the stream between a
+ * pass that spans GPUs and its neighbours.  shard_bytes must be a multiple of the device's
+ * mapping granularity (2 MiB). */
+typedef struct aqs_flat_s* aqs_flat_t;
+int aqs_flat_create(uint64_t shard_bytes, int world, int rank, aqs_flat_t* out, int* fd_out);
+int aqs_flat_attach(aqs_flat_t f, int peer_rank, int fd);
+int aqs_flat_ptr(aqs_flat_t f, void** base, void** own_shard);
+int aqs_flat_destroy(aqs_flat_t f);
+int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t first, uint64_t count, int rank, int log2_world);
+int aqs_plan_pass_span(aqs_plan_t p, uint64_t index, int log2_world, int* rank_bits_in_tile);
+
 /* ---- timing (CUDA events on the state's stream) ---------------------------- */
 int aqs_timer_create(aqs_timer_t* out);
 int aqs_timer_start(aqs_timer_t t, aqs_state_t s);

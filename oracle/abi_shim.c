@@ -216,6 +216,14 @@ int aqs_peer_bitswap(aqs_state_t s, void* const* members, int k, const int* loca
     return AQS_OK;
 }
 
+/* flat multi-GPU address space: CUDA virtual memory management has no CPU counterpart */
+int aqs_flat_create(uint64_t b, int w, int r, aqs_flat_t* o, int* fd) { (void)b; (void)w; (void)r; (void)o; (void)fd; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
+int aqs_flat_attach(aqs_flat_t f, int r, int fd) { (void)f; (void)r; (void)fd; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
+int aqs_flat_ptr(aqs_flat_t f, void** b, void** o) { (void)f; (void)b; (void)o; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
+int aqs_flat_destroy(aqs_flat_t f) { (void)f; return AQS_OK; }
+int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t a, uint64_t c, int r, int g) { (void)s; (void)p; (void)a; (void)c; (void)r; (void)g; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
+int aqs_plan_pass_span(aqs_plan_t p, uint64_t i, int g, int* out) { (void)p; (void)i; (void)g; if (out) *out = 0; return AQS_OK; }
+
 int aqs_timer_create(aqs_timer_t* out) { REQ(out, "null"); *out = (aqs_timer_t)calloc(1, sizeof **out); return AQS_OK; }
 int aqs_timer_start(aqs_timer_t t, aqs_state_t s) { (void)s; clock_gettime(CLOCK_MONOTONIC, &t->a); return AQS_OK; }
 int aqs_timer_stop(aqs_timer_t t, aqs_state_t s) { (void)s; clock_gettime(CLOCK_MONOTONIC, &t->b); return AQS_OK; }

@@ -95,6 +95,29 @@ def worker(rank, world, backend, port):
         st.run(plan)
         assert orc.rel_l2(st.gather(), want) < TOL
         st.set_basis(0)
+    # flat address space (GPUs only): one fused plan over the whole state, tiles that span GPUs go over NVLink
+    if backend == "cuda" and world > 1:
+        n = 19 + g
+        u = np.random.default_rng(11).random(300, dtype=np.float32)
+        for name, circ in (("random", _random_circuit(orc, n, 160, 6)), ("brickwork", orc.Circ(n, wl.brickwork(n, 8))),
+                           ("qft", orc.Circ(n, wl.qft(n))), ("ghz", orc.Circ(n, wl.ghz(n)))):
+            st = ShardedState(n, device=device)
+            assert st.flat_state is not None, "the flat address space should be available between the GPUs of one node"
+            x = 0 if name != "qft" else 0b1011001110100110101 & ((1 << n) - 1)
+            st.set_basis(x)
+            plan = st.compile(lower_array(circ))
+            st.run(plan)
+            want = orc.simulate(orc.new_state(n, x), circ)
+            err = orc.rel_l2(st.gather(), want)
+            assert err < TOL, (name, err)
+            assert plan.n_exchanges > 0, name           # some pass had a rank bit in its tile
+            if name == "ghz":
+                assert np.array_equal(st.gather(), want)
+            assert np.array_equal(st.sample(u), orc.sample(st.gather(), u, "exact")), name
+            st.set_basis(x)                              # a compiled plan is reusable
+            st.run(plan)
+            assert orc.rel_l2(st.gather(), want) < TOL, name
+            del plan, st
     # 2. BASELINE circuits: brickwork and QFT (QFT's CPhase ladder needs no exchange beyond the g H gates)
     n = 12
     st = ShardedState(n, device=device)

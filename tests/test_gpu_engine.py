@@ -364,3 +364,31 @@ def test_error_paths():
         eng.State(0)
     with pytest.raises(eng.EngineError):
         s.run(eng.Plan(5, eng.make_ops(0)))
+
+
+# ---- sharded pass launches (aqs_plan_run_shard) on ONE GPU ----------------------------------------
+# The R ranks of a flat multi-GPU state each run 1/R of the tiles of every pass.  On one GPU the
+# ranks can be played one after the other on the same buffer: the union must be the ordinary run.
+@pytest.mark.parametrize("n,g,seed", [(14, 1, 1), (15, 2, 2), (16, 3, 3), (18, 3, 4), (20, 2, 5)])
+def test_sharded_pass_launches_cover_every_tile_once(n, g, seed):
+    circ = random_circuit(n, 120, seed)
+    init = random_state(n, seed)
+    ops = lower_array(circ)
+    plan = eng.Plan(n, ops, eng.PLAN_FUSE)
+    n_passes = int(plan.info()["n_fused_passes"])
+    assert n_passes > 0
+    spans = [plan.pass_span(i, g) for i in range(n_passes)]
+    assert any(spans), "the random circuit should put a rank bit into some tile"
+    whole = eng.State(n)
+    whole.upload(init)
+    whole.run(plan)
+    want = whole.download()
+    s = eng.State(n)
+    s.upload(init)
+    order = np.random.default_rng(seed).permutation(1 << g)
+    for i in range(n_passes):
+        for r in order:
+            s.run_shard(plan, i, 1, int(r), g)
+    got = s.download()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert orc.rel_l2(got, orc.simulate(init.copy(), circ)) < TOL
