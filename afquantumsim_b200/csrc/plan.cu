@@ -48,6 +48,9 @@ struct POp {
     bool diag = false;       // m[0] diagonal and mux == -1: never constrains a tile
     bool dead = false;
     cd m[2][4];              // row-major 2x2
+    cd pre = cd(1, 0);       // diag(1, pre) is applied BEFORE m (both branches): a diagonal gate on the target folded
+                             // into this op as a phase on the target-bit-1 amplitude (absorb_diagonals)
+    cd gs = cd(1, 0);        // scalar that came with it (diag(d0, d1) = d0 * diag(1, d1/d0)): goes to the pass-wide scale
 };
 
 struct FusedPass {
@@ -238,6 +241,14 @@ static int pop_cost2(const POp& o) {
     return o.mux < 0 ? pair_cost(o.m[0], o.m[0]) : pair_cost(o.m[0], o.m[1]);
 }
 
+// does some branch of the op need the direct 8-instruction form?
+static bool is_general(const POp& o) {
+    if (o.diag) return false;
+    for (int v = 0; v < (o.mux >= 0 ? 2 : 1); ++v)
+        if (!mat_is_identity(o.m[v]) && decompose(o.m[v]).kind == TK_GEN) return true;
+    return false;
+}
+
 // bits on which the op acts NON-diagonally / diagonally
 static inline uint64_t nd_bits(const POp& c) { return c.diag ? 0ull : (1ull << c.p); }
 static inline uint64_t d_bits(const POp& c) {
@@ -259,6 +270,51 @@ static POp from_canon(const CanonOp& c) {
     o.diag = (c.kind == AQS_OP_DIAG);
     mat_identity(o.m[1]);
     return o;
+}
+
+// can the op carry a phase on y inside its butterflies?  (uncontrolled; every branch an in-place shear of one family)
+static bool takes_pre(const POp& z) {
+    if (z.diag || z.cmask) return false;
+    int kind = -1;
+    for (int v = 0; v < (z.mux >= 0 ? 2 : 1); ++v) {
+        if (mat_is_identity(z.m[v])) continue;
+        const Decomp d = decompose(z.m[v]);
+        if (d.kind > TK_SHI || (kind >= 0 && d.kind != kind)) return false;
+        kind = d.kind;
+    }
+    return kind >= 0;
+}
+
+// An uncontrolled diagonal gate diag(d0, d1) on qubit t (RotZ, Phase, Z, ...) commutes with everything that touches t
+// only as a control or diagonally, so it can slide forward to the next butterfly on t and ride inside it as a
+// factor on that op's y amplitudes (TF_CY: 4 scalar instructions per pair instead of an op of its own — in
+// brickwork circuits a third of all tile ops were such phases).  d0 goes to the pass-wide scale.
+static void absorb_diagonals(std::vector<POp>& ops) {
+    if (std::getenv("AQS_PLAN_NO_ABSORB")) return;
+    const size_t kLook = 4096;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        POp& w = ops[i];
+        if (w.dead || !w.diag || w.cmask || w.mux >= 0) continue;
+        const cd d0 = w.m[0][0], d1 = w.m[0][3];
+        if (std::abs(d0) < 1e-12) continue;
+        const uint64_t tb = 1ull << w.p;
+        for (size_t j = i + 1; j < ops.size() && j < i + kLook; ++j) {
+            POp& z = ops[j];
+            if (z.dead) continue;
+            if (!(nd_bits(z) & tb)) continue;            // touches t diagonally or not at all: w slides past it
+            if (takes_pre(z)) {
+                z.pre *= d1 / d0;
+                z.gs *= d0;
+                w.dead = true;
+            }
+            break;
+        }
+    }
+    std::vector<POp> kept;
+    kept.reserve(ops.size());
+    for (POp& o : ops)
+        if (!o.dead) kept.push_back(o);
+    ops.swap(kept);
 }
 
 static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
@@ -295,7 +351,9 @@ static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
                 POp prod = w;
                 mat_mul(u.m[0], w.m[0], prod.m[0]);
                 if (w.mux >= 0) mat_mul(u.m[0], w.m[1], prod.m[1]);
-                if (pop_cost2(prod) <= pop_cost2(w) + pop_cost2(u)) {
+                // (a diagonal u that would turn w into a general matrix stays separate: it may still ride
+                // inside the NEXT butterfly on this qubit as a phase, absorb_diagonals)
+                if (pop_cost2(prod) <= pop_cost2(w) + pop_cost2(u) && !(u.diag && is_general(prod) && !is_general(w))) {
                     w = prod;
                     return;
                 }
@@ -303,7 +361,7 @@ static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
                 // pending diagonal w, non-diagonal u: w may slide forward to u (ops in between touch t only diagonally)
                 POp prod = u;
                 mat_mul(u.m[0], w.m[0], prod.m[0]);
-                if (pop_cost2(prod) <= pop_cost2(w) + pop_cost2(u)) {
+                if (pop_cost2(prod) <= pop_cost2(w) + pop_cost2(u) && !(is_general(prod) && !is_general(u))) {
                     w.dead = true;
                     open[t] = -1;
                     append(prod);
@@ -407,6 +465,7 @@ static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
             kept.push_back(o);
         }
     }
+    absorb_diagonals(kept);
     return kept;
 }
 
@@ -627,7 +686,8 @@ struct Emitter {
     // families, purely imaginary ones (the X * RotX family) for TK_SHI.
     // butterfly of one decomposition under controls (cm, cv); d0 != nullptr: multiplexed on `mux_bit`
     // (d applies where the bit is 1, *d0 where it is 0) — both must be the same shear kind
-    void emit_butterfly(const Decomp& d, const Decomp* d0, int mux_bit, int tk, uint64_t cm, uint64_t cv) const {
+    // `pre` != 1 (shears only): diag(1, pre) applied first, i.e. the factor on y becomes complex (TF_CY)
+    void emit_butterfly(const Decomp& d, const Decomp* d0, int mux_bit, int tk, uint64_t cm, uint64_t cv, cd pre = cd(1, 0)) const {
         TileOp t;
         std::memset(&t, 0, sizeof t);
         t.kind = (uint8_t)d.kind;
@@ -645,6 +705,13 @@ struct Emitter {
             if (d.sy != 1.0 || d.sx != 1.0 || d.pre_imag || (d0 && (d0->sy != 1.0 || d0->sx != 1.0 || d0->pre_imag))) t.flags |= TF_PY;
             if (d.pre_imag) t.flags |= TF_IMAG_A;
             if (d0 && d0->pre_imag) t.flags |= TF_IMAG_B;
+            if (pre != cd(1, 0)) {
+                const cd fa = cd(d.sy, 0) * (d.pre_imag ? cd(0, 1) : cd(1, 0)) * pre;
+                const cd fb = d0 ? cd(d0->sy, 0) * (d0->pre_imag ? cd(0, 1) : cd(1, 0)) * pre : fa;
+                t.a[3] = (float)fa.real(); t.qy[0] = (float)fa.imag();
+                t.b[3] = (float)fb.real(); t.qy[1] = (float)fb.imag();
+                t.flags |= TF_PY | TF_CY;
+            }
         }
         if (d0) {
             // the multiplexing bit: register -> pair subsets; thread / outside the tile -> predicate picks the set
@@ -691,9 +758,15 @@ struct Emitter {
         }
         push(t);
     }
-    void emit_matrix(const cd* M, int bit, int tk, uint64_t cm, uint64_t cv, cd* pass_scale = nullptr) const {
-        if (mat_is_identity(M)) return;
+    void emit_matrix(const cd* M, int bit, int tk, uint64_t cm, uint64_t cv, cd* pass_scale = nullptr, cd pre = cd(1, 0)) const {
+        if (mat_is_identity(M) && pre == cd(1, 0)) return;
         Decomp d = decompose(M);
+        if (pre != cd(1, 0) && (d.kind > TK_SHI || cm)) {
+            // no in-place form to carry the phase: multiply it into the matrix
+            cd M2[4] = {M[0], M[1] * pre, M[2], M[3] * pre};
+            emit_matrix(M2, bit, tk, cm, cv, pass_scale);
+            return;
+        }
         (void)bit;
         if (d.kind <= TK_SHI && d.rho != 1.0) {
             // the common modulus of an uncontrolled op is a global factor; a controlled one keeps it in its prescale
@@ -714,7 +787,7 @@ struct Emitter {
                 for (int i = 0; i < 4; ++i) { d.c[2 * i] = (float)M[i].real(); d.c[2 * i + 1] = (float)M[i].imag(); }
             }
         }
-        emit_butterfly(d, nullptr, -1, tk, cm, cv);
+        emit_butterfly(d, nullptr, -1, tk, cm, cv, pre);
     }
     void emit(const POp& o, cd& pass_scale) const {
         const uint64_t tb = 1ull << o.p;
@@ -735,6 +808,12 @@ struct Emitter {
         const int tk = L->reg_of[local_of_bit[o.p]];
         cd m0[4], m1[4];
         for (int i = 0; i < 4; ++i) { m0[i] = o.m[0][i]; m1[i] = o.m[o.mux < 0 ? 0 : 1][i]; }
+        cd pre = o.pre;
+        if (pre != cd(1, 0) && o.cmask != 0) {           // (absorb_diagonals only picks uncontrolled ops)
+            for (int i = 1; i < 4; i += 2) { m0[i] *= pre; m1[i] *= pre; }
+            pre = cd(1, 0);
+        }
+        if (o.cmask == 0) pass_scale *= o.gs;
         if (o.cmask == 0) {
             // a common factor -1 / +-i that makes the decompositions cheaper is a global phase
             cd f(1, 0);
@@ -745,7 +824,7 @@ struct Emitter {
             }
         }
         if (o.mux < 0) {
-            emit_matrix(m0, o.p, tk, o.cmask, o.cval, o.cmask == 0 ? &pass_scale : nullptr);
+            emit_matrix(m0, o.p, tk, o.cmask, o.cval, o.cmask == 0 ? &pass_scale : nullptr, pre);
             return;
         }
         const uint64_t mb = 1ull << o.mux;
@@ -760,9 +839,11 @@ struct Emitter {
             pass_scale *= common;
             d1.sx *= d1.rho / common; d1.sy *= d1.rho / common;
             d0.rho = d1.rho = 1.0;
-            emit_butterfly(d1, &d0, o.mux, tk, 0, 0);
+            emit_butterfly(d1, &d0, o.mux, tk, 0, 0, pre);
             return;
         }
+        if (pre != cd(1, 0))
+            for (int i = 1; i < 4; i += 2) { m0[i] *= pre; m1[i] *= pre; }
         emit_matrix(m0, o.p, tk, o.cmask | mb, o.cval);
         emit_matrix(m1, o.p, tk, o.cmask | mb, o.cval | mb);
     }
@@ -998,6 +1079,8 @@ static int ensure_uploaded(aqs_plan_s* p) {
             d.sx_a = t.sx[0];
             d.sx_b = t.sx[1];
             d.mask = t.mask;
+            if (t.flags & TF_CY) std::memcpy(&d.mask, &t.qy[0], sizeof(float));   // shears never read the pair mask
+            d.qy_b = t.qy[1];
             d.tpred = (uint32_t)t.t_mask | ((uint32_t)t.t_val << 16);
             d.b_mask = t.b_mask;
             d.b_val = t.b_val;

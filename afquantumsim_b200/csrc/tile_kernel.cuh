@@ -69,7 +69,9 @@ enum TileFlags : uint8_t {
     TF_PY = 8,       // shears: each set carries factors (sx, sy) applied first to x and y: reflections (CX
                      // folded into a rotation) and sign fixes ride inside the op.  sy = c[3]; sx = TileOp.sx[set]
     TF_IMAG_A = 16,  // TK_SHI with TF_PY: set a's factors are i*sx, i*sy (the X * RotX family)
-    TF_IMAG_B = 32   // same for set b
+    TF_IMAG_B = 32,  // same for set b
+    TF_CY = 64       // (with TF_PY) the factor on y is complex, sy + i*qy per set: a diagonal gate that precedes the op on
+                     // its target qubit (RotZ, Phase, ...) rides inside it as a phase on y; the x factor is as without TF_CY
 };
 
 struct alignas(16) TileOp {
@@ -88,15 +90,18 @@ struct alignas(16) TileOp {
     float sx[2];         // TF_PY: factor on x for set a / set b
     float a[8];          // coefficient set used where the predicate holds
     float b[8];          // TF_MUX: coefficient set used where it does not
+    float qy[2];         // TF_CY: imaginary part of the factor on y for set a / set b
+    uint32_t pad[2];
 };
-static_assert(sizeof(TileOp) == 96, "TileOp layout");
+static_assert(sizeof(TileOp) == 112, "TileOp layout");
 
 // dispatch code = group * 8 + sub:
-//   shears:  group = kind * 5 + tk (+ 10 with TF_PY)  (0..19),  sub = mj (0..4)
+//   shears:  group = kind * 5 + tk (+ 10 with TF_PY)  (0..19),  sub = mj (0..4);  TK_SHR with TF_CY: group = 32 + tk
 //   direct:  group = 20 + kind - TK_GEN (20..22),                sub = tk
 //   factors: group = 23 + (kind - TK_PHASE) * 2 + hi (23..30),   sub = pattern & 7, pattern = mj (0..6) or mj - 1 (7..11), hi = pattern >> 3
 __host__ __device__ constexpr uint32_t tile_op_code(uint32_t kind, uint32_t tk, uint32_t mj, uint32_t flags) {
-    return kind <= 1 ? ((kind * 5u + tk + ((flags & 8u) ? 10u : 0u)) << 3) | mj
+    return kind == 0 && (flags & 64u) ? ((32u + tk) << 3) | mj
+         : kind <= 1 ? ((kind * 5u + tk + ((flags & 8u) ? 10u : 0u)) << 3) | mj
          : kind <= 4 ? ((20u + kind - 2u) << 3) | tk
                      : ((23u + (kind - 5u) * 2u + ((mj >= 8u ? mj - 1u : mj) >> 3)) << 3) | ((mj >= 8u ? mj - 1u : mj) & 7u);
 }
@@ -121,18 +126,18 @@ static_assert(sizeof(TileSeg) == 64, "TileSeg layout");
 // four of them per op in a chain made the whole kernel latency-bound.
 struct alignas(16) DevOp {
     uint32_t word;       // tile_op_code(kind, tk, mj) | flags << 16
-    uint32_t mask;
+    uint32_t mask;       // shears (which resolve pair subsets at compile time) keep qy of set a here instead (float bits)
     uint32_t tpred;      // t_mask | t_val << 16
     float sx_a;          // TF_PY: factor on x, set a
     uint32_t b_mask;
     uint32_t b_val;
     float sx_b;          // TF_PY: factor on x, set b
-    uint32_t pad1;
+    float qy_b;          // TF_CY: imaginary part of the factor on y, set b
     float a[4];          // TK_GEN: c[0..3]
     float b[4];          // TK_GEN: c[4..7]
 };
 static_assert(sizeof(DevOp) == 64, "DevOp layout");
-constexpr uint32_t kDevOpEnd = 0xffu;   // group value of the sentinel that follows the last op
+constexpr uint32_t kDevOpEnd = 0x3fu;   // group value of the sentinel that follows the last op
 
 struct alignas(16) PassParams {
     float2* state;
@@ -210,12 +215,18 @@ struct ShearCoef {
     float qy, qx;      // TK_SHI with a prescale: the factors are (sx + i qx), (sy + i qy)
 };
 
-template <int KIND, bool PY>
+template <int KIND, int PY>
 __device__ __forceinline__ void shear(f2& x, f2& y, const ShearCoef& k) {
     if (KIND == TK_SHR) {
-        if (PY) {
+        if (PY == 1) {
             x = mul2(bc(k.sx), x);
             y = mul2(bc(k.sy), y);
+        } else if (PY == 2) {
+            // y *= sy + i*qy (a diagonal gate folded into the op), x *= sx
+            x = mul2(bc(k.sx), x);
+            const float yr = lo(y), yi = hi(y);
+            const float ty = yr * k.sy - yi * k.qy;
+            y = pk(ty, fmaf(yr, k.qy, yi * k.sy));
         }
         asm("{\n\t.reg .b64 ka, kb, kg;\n\t"
             "mov.b64 ka, {%2, %2};\n\tmov.b64 kb, {%3, %3};\n\tmov.b64 kg, {%4, %4};\n\t"
@@ -283,7 +294,7 @@ __device__ __forceinline__ void butterfly_direct(f2& x, f2& y, const float (&c)[
 
 // Pairs whose pair-index bit J is set use ka, the others kb (ops that need any other subset of the
 // pairs are emitted as TK_GEN by the planner).
-template <int KIND, int TK, int J, bool PY>
+template <int KIND, int TK, int J, int PY>
 __device__ __forceinline__ void apply_shear(f2 (&a)[kRegs], const ShearCoef& ka, const ShearCoef& kb) {
 #pragma unroll
     for (int p = 0; p < kPairs; ++p) {
@@ -346,24 +357,25 @@ __device__ __forceinline__ void load_head(OpHead& hd, const DevOp& op) {
 }
 
 // Class preludes, one copy each in the interpreter loop: predicate, coefficient sets, header of the next op.
-__device__ __forceinline__ ShearCoef make_coef(bool shi_py, float a, float b, float g, float sy, float sx, bool imag) {
+__device__ __forceinline__ ShearCoef make_coef(bool shi_py, float a, float b, float g, float sy, float sx, bool imag, bool cy, float qy) {
     ShearCoef k;
     k.a = a; k.b = b; k.g = g;
     const bool im = shi_py && imag;
     k.sx = im ? 0.f : sx; k.qx = im ? sx : 0.f;
-    k.sy = im ? 0.f : sy; k.qy = im ? sy : 0.f;
+    k.sy = (im && !cy) ? 0.f : sy; k.qy = cy ? qy : (im ? sy : 0.f);
     return k;
 }
 __device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint32_t tid, uint32_t tile_no, ShearCoef& ka, ShearCoef& kb) {
     const uint32_t flags = hd.h.x >> 16;
-    const bool py = (flags & TF_PY) != 0;
-    const bool shi_py = py && (((hd.h.x >> 3) & 0x1fu) >= 15u);
-    ka = make_coef(shi_py, hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0);
+    const bool py = (flags & TF_PY) != 0, cy = (flags & TF_CY) != 0;
+    const uint32_t grp = (hd.h.x >> 3) & 0x3fu;
+    const bool shi_py = py && grp >= 15u && grp < 20u;
+    ka = make_coef(shi_py, hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0, cy, __uint_as_float(hd.h.y));
     kb = ka;
     bool run = true;
     if (flags & (TF_PRED | TF_REGMUX)) {
         const float4 cb = *reinterpret_cast<const float4*>(&op.b[0]);
-        const ShearCoef kset_b = make_coef(shi_py, cb.x, cb.y, cb.z, cb.w, py ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0);
+        const ShearCoef kset_b = make_coef(shi_py, cb.x, cb.y, cb.z, cb.w, py ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0, cy, op.qy_b);
         bool use_b;
         run = op_predicate(op, flags, hd.h.z, tid, tile_no, use_b);
         if (use_b) ka = kset_b;
@@ -477,7 +489,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
         load_head(hd, sops[first]);
         for (uint32_t o = first; o < end; ++o) {
             const DevOp& op = sops[o];          // every body leaves the header of op o + 1 in hd (the sentinel keeps it in bounds)
-            const uint32_t word = hd.h.x, sub = word & 7u, grp = (word >> 3) & 0x1fu;
+            const uint32_t word = hd.h.x, sub = word & 7u, grp = (word >> 3) & 0x3fu;
 #define AQS_SH(K, TKV, PYV)                                                          \
     do {                                                                             \
         if (sub & 2u) { if (sub & 1u) apply_shear<K, TKV, 3, PYV>(a, ka, kb); else apply_shear<K, TKV, 2, PYV>(a, ka, kb); } \
@@ -504,16 +516,18 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
             else { if (sub & 1u) apply_factor<K, 10>(a, fr, fi, mask); else apply_factor<K, 9>(a, fr, fi, mask); }    \
         }                                                                                                      \
     } while (0)
-            if (grp < 20u) {
-                // shears: grp = kind * 5 + tk (+ 10 with a prescale)
+            if (grp < 20u || grp >= 32u) {
+                // shears: grp = kind * 5 + tk (+ 10 with a prescale); 32 + tk: real shears, complex factor on y
                 ShearCoef ka, kb;
                 if (!shear_prelude(op, hd, tid, tile_no, ka, kb)) continue;
-                if (grp < 10u) {
-                    if (grp < 5u) AQS_SH5(TK_SHR, false, grp);
-                    else AQS_SH5(TK_SHI, false, grp - 5u);
+                if (grp >= 32u) {
+                    AQS_SH5(TK_SHR, 2, grp - 32u);
+                } else if (grp < 10u) {
+                    if (grp < 5u) AQS_SH5(TK_SHR, 0, grp);
+                    else AQS_SH5(TK_SHI, 0, grp - 5u);
                 } else {
-                    if (grp < 15u) AQS_SH5(TK_SHR, true, grp - 10u);
-                    else AQS_SH5(TK_SHI, true, grp - 15u);
+                    if (grp < 15u) AQS_SH5(TK_SHR, 1, grp - 10u);
+                    else AQS_SH5(TK_SHI, 1, grp - 15u);
                 }
             } else {
                 bool use_b;

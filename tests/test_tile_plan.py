@@ -88,7 +88,26 @@ def test_cx_folds_into_rotations():
     n_gates = len(wl.brickwork(n, 10))
     assert len(kinds) < 0.75 * n_gates, (len(kinds), n_gates)
     assert sum(k in (te.PERM_R, te.PERM_I) for k in kinds) < 0.15 * len(kinds)
-    assert sum(k == te.GEN for k in kinds) < 0.1 * len(kinds)      # edge qubits: rotations with no CX between them merge
+    assert sum(k == te.GEN for k in kinds) < 0.15 * len(kinds)     # edge qubits: rotations with no CX between them merge
+
+
+def test_diagonal_gates_ride_inside_the_next_butterfly():
+    """brickwork: a RotZ slides forward to the next rotation / multiplexed CX on its qubit and becomes that op's
+    complex factor on y (TF_CY) instead of a phase op of its own"""
+    n = 14
+    gates = wl.brickwork(n, 10)
+    plan = eng.Plan(n, lower_array(orc.Circ(n, gates)), eng.PLAN_FUSE)
+    ops = []
+    for i in range(plan.info()["n_fused_passes"]):
+        ops += te.parse(plan.export_pass(i))[2]
+    n_rotz = sum(g[0] == "RotZ" for g in gates)
+    n_phase = sum(op.kind in (te.PHASE, te.PHASE_N) for op in ops)
+    n_cy = sum(bool(op.flags & te.TF_CY) for op in ops)
+    assert n_rotz > 30 and n_cy > 0.5 * n_rotz, (n_rotz, n_cy)
+    assert n_phase < 0.35 * n_rotz, (n_rotz, n_phase)
+    assert all(op.kind <= te.SHI and op.flags & te.TF_PY for op in ops if op.flags & te.TF_CY)
+    init = random_state(n, 11)
+    assert orc.rel_l2(te.run_plan(plan, init), orc.simulate(init.copy(), orc.Circ(n, gates))) < TOL
 
 
 def test_descriptor_budget_splits_passes():

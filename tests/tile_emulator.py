@@ -13,7 +13,7 @@ import numpy as np
 
 K_LANE, K_REG, K_MAX_THREAD_BITS, K_MAX_BITS = 5, 5, 8, 38
 SHR, SHI, GEN, PERM_R, PERM_I, PHASE, SCALE_R, SCALE_I, PHASE_N = range(9)
-TF_MUX, TF_REGMUX, TF_PRED, TF_PY, TF_IMAG_A, TF_IMAG_B = 1, 2, 4, 8, 16, 32
+TF_MUX, TF_REGMUX, TF_PRED, TF_PY, TF_IMAG_A, TF_IMAG_B, TF_CY = 1, 2, 4, 8, 16, 32, 64
 
 
 class BitList(ctypes.Structure):
@@ -39,10 +39,10 @@ class TileOp(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_uint8), ("tk", ctypes.c_uint8), ("flags", ctypes.c_uint8), ("mj", ctypes.c_uint8),
                 ("mask", ctypes.c_uint32), ("t_mask", ctypes.c_uint16), ("t_val", ctypes.c_uint16), ("code", ctypes.c_uint32),
                 ("b_mask", ctypes.c_uint32), ("b_val", ctypes.c_uint32), ("sx", ctypes.c_float * 2),
-                ("a", ctypes.c_float * 8), ("b", ctypes.c_float * 8)]
+                ("a", ctypes.c_float * 8), ("b", ctypes.c_float * 8), ("qy", ctypes.c_float * 2), ("pad", ctypes.c_uint32 * 2)]
 
 
-assert ctypes.sizeof(TileSeg) == 64 and ctypes.sizeof(TileOp) == 96
+assert ctypes.sizeof(TileSeg) == 64 and ctypes.sizeof(TileOp) == 112
 
 
 def parse(raw: bytes):
@@ -83,7 +83,7 @@ def deposit(j, positions):
     return j
 
 
-def butterfly(kind, x, y, c, py=False, sx=1.0, imag=False):
+def butterfly(kind, x, y, c, py=False, sx=1.0, imag=False, cy=False, qy=0.0):
     """the kernel's in-place sequences, in float32 (tile_kernel.cuh shear<> / butterfly_direct<>)"""
     f = np.float32
     c = [f(v) for v in c]
@@ -91,9 +91,13 @@ def butterfly(kind, x, y, c, py=False, sx=1.0, imag=False):
         if imag:
             assert kind == SHI
             x = x * (np.complex64(1j) * f(sx))
-            y = y * (np.complex64(1j) * c[3])
         else:
             x = x * f(sx)
+        if cy:
+            y = y * np.complex64(complex(c[3], f(qy)))       # TF_CY: explicit complex factor on y
+        elif imag:
+            y = y * (np.complex64(1j) * c[3])
+        else:
             y = y * c[3]
     if kind == SHR:
         x = x + c[0] * y
@@ -116,6 +120,8 @@ def butterfly(kind, x, y, c, py=False, sx=1.0, imag=False):
 
 def op_code(kind, tk, mj, flags):
     """tile_kernel.cuh tile_op_code"""
+    if kind == 0 and flags & TF_CY:
+        return ((32 + tk) << 3) | mj
     if kind <= 1:
         return ((kind * 5 + tk + (10 if flags & TF_PY else 0)) << 3) | mj
     if kind <= 4:
@@ -248,9 +254,14 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
                     continue
                 # kernel: ka = (mux && !ok) ? b : a;  kb = regmux ? b : ka;  pair subset picks ka / kb;
                 # threads with !ok and no mux skip the op
-                py = bool(op.flags & TF_PY)
-                xa, ya = butterfly(op.kind, x, y, ca, py, op.sx[0], bool(op.flags & TF_IMAG_A))
-                xb, yb = butterfly(op.kind, x, y, cb, py, op.sx[1], bool(op.flags & TF_IMAG_B))
+                py, cy = bool(op.flags & TF_PY), bool(op.flags & TF_CY)
+                assert py or not cy, "TF_CY needs TF_PY"
+                if not (mux or regmux):
+                    cb, sxb, qyb = ca, op.sx[0], op.qy[0]       # kernel: kb = ka for a plain op
+                else:
+                    sxb, qyb = op.sx[1], op.qy[1]
+                xa, ya = butterfly(op.kind, x, y, ca, py, op.sx[0], bool(op.flags & TF_IMAG_A), cy, op.qy[0])
+                xb, yb = butterfly(op.kind, x, y, cb, py, sxb, bool(op.flags & (TF_IMAG_B if (mux or regmux) else TF_IMAG_A)), cy, qyb)
                 if regmux:
                     xs, ys = (xa, ya) if pair_uses_a(op, p) else (xb, yb)
                     a[:, :, k0] = np.where(ok, xs, x)
