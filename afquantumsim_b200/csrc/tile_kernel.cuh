@@ -96,11 +96,13 @@ struct alignas(16) TileOp {
 static_assert(sizeof(TileOp) == 112, "TileOp layout");
 
 // dispatch code = group * 8 + sub:
-//   shears:  group = kind * 5 + tk (+ 10 with TF_PY)  (0..19),  sub = mj (0..4);  TK_SHR with TF_CY: group = 32 + tk
+//   shears:  group = kind * 5 + tk (+ 10 with TF_PY)  (0..19),  sub = mj (0..4);  TK_SHR with TF_CY: group = 32 + tk;
+//            TK_SHI with TF_CY and real factors on x: group = 37 + tk
 //   direct:  group = 20 + kind - TK_GEN (20..22),                sub = tk
 //   factors: group = 23 + (kind - TK_PHASE) * 2 + hi (23..30),   sub = pattern & 7, pattern = mj (0..6) or mj - 1 (7..11), hi = pattern >> 3
 __host__ __device__ constexpr uint32_t tile_op_code(uint32_t kind, uint32_t tk, uint32_t mj, uint32_t flags) {
     return kind == 0 && (flags & 64u) ? ((32u + tk) << 3) | mj
+         : kind == 1 && (flags & 64u) && !(flags & 48u) ? ((37u + tk) << 3) | mj
          : kind <= 1 ? ((kind * 5u + tk + ((flags & 8u) ? 10u : 0u)) << 3) | mj
          : kind <= 4 ? ((20u + kind - 2u) << 3) | tk
                      : ((23u + (kind - 5u) * 2u + ((mj >= 8u ? mj - 1u : mj) >> 3)) << 3) | ((mj >= 8u ? mj - 1u : mj) & 7u);
@@ -236,7 +238,13 @@ __device__ __forceinline__ void shear(f2& x, f2& y, const ShearCoef& k) {
         // x += i*a*y etc. on the halves with scalar FFMA (same FMA-pipe time as three FFMA2; the packed
         // form needs (-c, c) operand pairs that ptxas keeps rebuilding with MOVs)
         float xr = lo(x), xi = hi(x), yr = lo(y), yi = hi(y);
-        if (PY) {
+        if (PY == 2) {
+            // real factor on x, complex factor on y (a diagonal gate folded into the op)
+            xr *= k.sx; xi *= k.sx;
+            const float ty = yr * k.sy - yi * k.qy;
+            yi = fmaf(yr, k.qy, yi * k.sy);
+            yr = ty;
+        } else if (PY) {
             // complex factors (real or purely imaginary in practice; the set decides at run time)
             const float tx = xr * k.sx - xi * k.qx;
             xi = fmaf(xr, k.qx, xi * k.sx);
@@ -521,7 +529,8 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
                 ShearCoef ka, kb;
                 if (!shear_prelude(op, hd, tid, tile_no, ka, kb)) continue;
                 if (grp >= 32u) {
-                    AQS_SH5(TK_SHR, 2, grp - 32u);
+                    if (grp < 37u) AQS_SH5(TK_SHR, 2, grp - 32u);
+                    else AQS_SH5(TK_SHI, 2, grp - 37u);
                 } else if (grp < 10u) {
                     if (grp < 5u) AQS_SH5(TK_SHR, 0, grp);
                     else AQS_SH5(TK_SHI, 0, grp - 5u);

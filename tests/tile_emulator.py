@@ -122,6 +122,8 @@ def op_code(kind, tk, mj, flags):
     """tile_kernel.cuh tile_op_code"""
     if kind == 0 and flags & TF_CY:
         return ((32 + tk) << 3) | mj
+    if kind == 1 and flags & TF_CY and not flags & (TF_IMAG_A | TF_IMAG_B):
+        return ((37 + tk) << 3) | mj
     if kind <= 1:
         return ((kind * 5 + tk + (10 if flags & TF_PY else 0)) << 3) | mj
     if kind <= 4:
