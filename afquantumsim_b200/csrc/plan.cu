@@ -50,6 +50,9 @@ struct POp {
     cd m[2][4];              // row-major 2x2
     cd pre = cd(1, 0);       // diag(1, pre) is applied BEFORE m (both branches): a diagonal gate on the target folded
                              // into this op as a phase on the target-bit-1 amplitude (absorb_diagonals)
+    std::vector<std::pair<int, cd>> ladder;   // non-empty: a LADDER of controlled phases with hub bit p (diag == true): the amplitudes
+                             // with bit p set are multiplied by m[0][3] and by w for every listed (bit, w) whose bit is 1;
+                             // cmask holds the listed bits (for the commutation rules only)
     cd gs = cd(1, 0);        // scalar that came with it (diag(d0, d1) = d0 * diag(1, d1/d0)): goes to the pass-wide scale
 };
 
@@ -319,6 +322,44 @@ static void absorb_diagonals(std::vector<POp>& ops) {
     ops.swap(kept);
 }
 
+// Runs of controlled phases diag(1, e^{i theta}) on ONE target, each under a single control — QFT's ladders
+// CPhase(j, i), j < i — become one TK_LADDER op (tile_kernel.cuh): one dispatch and ~2.5 butterflies' worth of
+// arithmetic instead of one phase op per control.
+static void group_ladders(std::vector<POp>& ops) {
+    if (std::getenv("AQS_PLAN_NO_LADDER")) return;
+    auto member = [](const POp& o) {
+        return !o.dead && o.diag && o.mux < 0 && o.ladder.empty() && z0(o.m[0][0] - 1.0) && popc(o.cmask) <= 1 && o.cval == o.cmask &&
+               std::fabs(std::abs(o.m[0][3]) - 1.0) < 1e-6;
+    };
+    std::vector<POp> out;
+    out.reserve(ops.size());
+    for (size_t i = 0; i < ops.size();) {
+        if (!member(ops[i])) { out.push_back(ops[i++]); continue; }
+        size_t j = i;
+        uint64_t used = 0;
+        int controlled = 0;
+        while (j < ops.size() && member(ops[j]) && ops[j].p == ops[i].p && !(ops[j].cmask & used)) {
+            used |= ops[j].cmask;
+            controlled += ops[j].cmask != 0;
+            ++j;
+        }
+        if (controlled < 3) { out.push_back(ops[i++]); continue; }
+        POp L;
+        L.p = ops[i].p;
+        L.diag = true;
+        mat_identity(L.m[0]);
+        mat_identity(L.m[1]);
+        for (size_t k = i; k < j; ++k) {
+            if (ops[k].cmask == 0) L.m[0][3] *= ops[k].m[0][3];
+            else L.ladder.push_back({__builtin_ctzll(ops[k].cmask), ops[k].m[0][3]});
+        }
+        L.cmask = L.cval = used;
+        out.push_back(L);
+        i = j;
+    }
+    ops.swap(out);
+}
+
 static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
     std::vector<POp> out;
     out.reserve(in.size() + 16);
@@ -495,6 +536,7 @@ static std::vector<POp> simplify(int n, const std::vector<CanonOp>& in) {
             }
         }
     }
+    group_ladders(kept);
     absorb_diagonals(kept);
     return kept;
 }
@@ -819,8 +861,60 @@ struct Emitter {
         }
         emit_butterfly(d, nullptr, -1, tk, cm, cv, pre);
     }
+    void emit_ladder(const POp& o) const {
+        const uint64_t tb = 1ull << o.p;
+        TileOp h;
+        std::memset(&h, 0, sizeof h);
+        h.kind = TK_LADDER;
+        uint32_t rm, rv;
+        select(tb, tb, rm, rv, h);                      // the hub: register bit -> register subset, else a predicate
+        h.mj = rm ? (uint8_t)__builtin_ctz(rm) : 5;
+        h.mask = 0;
+        for (uint32_t k = 0; k < (uint32_t)kRegs; ++k)
+            if ((k & rm) == rv) h.mask |= 1u << k;
+        h.a[0] = (float)o.m[0][3].real();
+        h.a[1] = (float)o.m[0][3].imag();
+        TileOp reg;                                     // factors of the controls on register bits
+        std::memset(&reg, 0, sizeof reg);
+        reg.kind = TK_LADDER_CONT;
+        for (int r = 0; r < 4; ++r) reg.a[2 * r] = 1.f;
+        reg.sx[0] = 1.f;
+        std::vector<TileOp> cont;
+        int fill = 4;
+        for (const auto& cw : o.ladder) {
+            const int j = local_of_bit[cw.first];
+            const float wr = (float)cw.second.real(), wi = (float)cw.second.imag();
+            if (j >= 0 && L->reg_of[j] >= 0) {
+                const int r = L->reg_of[j];
+                if (r < 4) { reg.a[2 * r] = wr; reg.a[2 * r + 1] = wi; }
+                else { reg.sx[0] = wr; reg.sx[1] = wi; }
+                continue;
+            }
+            if (fill == 4) {
+                TileOp c;
+                std::memset(&c, 0, sizeof c);
+                c.kind = TK_LADDER_CONT;
+                c.mask = 0x3f3f3f3fu;
+                for (int q = 0; q < 4; ++q) c.a[2 * q] = 1.f;
+                cont.push_back(c);
+                fill = 0;
+            }
+            TileOp& c = cont.back();
+            const uint32_t code = (j >= 0) ? (uint32_t)L->thr_of[j] : (0x20u | (uint32_t)block_bit[cw.first]);
+            c.mask = (c.mask & ~(0xffu << (8 * fill))) | (code << (8 * fill));
+            c.a[2 * fill] = wr;
+            c.a[2 * fill + 1] = wi;
+            ++fill;
+        }
+        const uint32_t n_cont = (uint32_t)cont.size();
+        std::memcpy(&h.sx[0], &n_cont, sizeof n_cont);
+        push(h);
+        push(reg);
+        for (TileOp& c : cont) push(c);
+    }
     void emit(const POp& o, cd& pass_scale) const {
         const uint64_t tb = 1ull << o.p;
+        if (!o.ladder.empty()) { emit_ladder(o); return; }
         if (o.diag) {
             const cd d0 = o.m[0][0], d1 = o.m[0][3];
             if (z0(d0 - 1.0)) {
@@ -965,7 +1059,7 @@ static int plan_variant(int n, int T, const std::vector<POp>& ops, int variant, 
             // whatever is left goes back to the candidates, in program order
             bool full = false;
             for (size_t i = 0; i < seg_taken.size(); ++i) {
-                if (fp.ops.size() + 4 > (size_t)kOpsLarge) {
+                if (fp.ops.size() + 4 + ops[seg_taken[i]].ladder.size() / 4 + 2 > (size_t)kOpsLarge) {
                     unplaced.assign(seg_taken.begin() + i, seg_taken.end());
                     std::vector<int> merged(unplaced.size() + seg_rest.size());
                     std::merge(unplaced.begin(), unplaced.end(), seg_rest.begin(), seg_rest.end(), merged.begin());
@@ -1114,7 +1208,7 @@ static int ensure_uploaded(aqs_plan_s* p) {
             d.tpred = (uint32_t)t.t_mask | ((uint32_t)t.t_val << 16);
             d.b_mask = t.b_mask;
             d.b_val = t.b_val;
-            for (int i = 0; i < 4; ++i) { d.a[i] = t.a[i]; d.b[i] = (t.kind == TK_GEN) ? t.a[4 + i] : t.b[i]; }
+            for (int i = 0; i < 4; ++i) { d.a[i] = t.a[i]; d.b[i] = (t.kind == TK_GEN || t.kind == TK_LADDER_CONT) ? t.a[4 + i] : t.b[i]; }
         }
         host[off++].word = kDevOpEnd << 3;   // sentinel: read by the prefetch, never executed
     }

@@ -60,7 +60,15 @@ enum TileKind : uint8_t {
     TK_PHASE = 5,    // unit-modulus factor e^{i theta}, |theta| <= pi/2:  c = {-tan(theta/2), sin(theta)}
     TK_SCALE_R = 6,  // real factor     c = {s}
     TK_SCALE_I = 7,  // imaginary factor i*s
-    TK_PHASE_N = 8   // -e^{i theta}: the same three shears with negated accumulators (pi/2 < |angle| <= pi)
+    TK_PHASE_N = 8,  // -e^{i theta}: the same three shears with negated accumulators (pi/2 < |angle| <= pi)
+    // A LADDER of controlled phases that share their target ("hub") qubit — QFT's CPhase(j, i) for all j < i — as
+    // ONE op: every selected amplitude is multiplied by  self * PROD_{controls c whose bit is 1} w_c,  |w_c| = 1.
+    // The header is followed by one TK_LADDER_CONT record with the factors of the controls that sit on register
+    // bits (a[0..7], sx[0..1] = w_0 .. w_4, (1, 0) where there is none) and by sx[0] (as an integer) further
+    // records with four thread / block controls each: byte q of `mask` = source of entry q (0..7: bit of
+    // threadIdx.x; 0x20 | b: bit b of the tile number; 0x3f: empty), a[2q], a[2q + 1] = w.
+    TK_LADDER = 9,
+    TK_LADDER_CONT = 10
 };
 enum TileFlags : uint8_t {
     TF_MUX = 1,      // threads/CTAs whose predicate is false use coefficient set b instead of skipping
@@ -100,10 +108,13 @@ static_assert(sizeof(TileOp) == 112, "TileOp layout");
 //            TK_SHI with TF_CY and real factors on x: group = 37 + tk
 //   direct:  group = 20 + kind - TK_GEN (20..22),                sub = tk
 //   factors: group = 23 + (kind - TK_PHASE) * 2 + hi (23..30),   sub = pattern & 7, pattern = mj (0..6) or mj - 1 (7..11), hi = pattern >> 3
+//   ladder:  group = 42, sub = mj (0..4: registers whose bit mj is set; 5: all registers);  its records: group 63
 __host__ __device__ constexpr uint32_t tile_op_code(uint32_t kind, uint32_t tk, uint32_t mj, uint32_t flags) {
     return kind == 0 && (flags & 64u) ? ((32u + tk) << 3) | mj
          : kind == 1 && (flags & 64u) && !(flags & 48u) ? ((37u + tk) << 3) | mj
          : kind <= 1 ? ((kind * 5u + tk + ((flags & 8u) ? 10u : 0u)) << 3) | mj
+         : kind == 9 ? (42u << 3) | mj
+         : kind == 10 ? (63u << 3)
          : kind <= 4 ? ((20u + kind - 2u) << 3) | tk
                      : ((23u + (kind - 5u) * 2u + ((mj >= 8u ? mj - 1u : mj) >> 3)) << 3) | ((mj >= 8u ? mj - 1u : mj) & 7u);
 }
@@ -352,6 +363,30 @@ __device__ __forceinline__ void apply_direct(f2 (&a)[kRegs], const float (&c)[8]
         if (mask >> p & 1u) butterfly_direct<KIND>(a[k0], a[k1], c);
     }
 }
+__host__ __device__ __forceinline__ constexpr int ctz_c(int i) { return (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : 4; }
+// Ladder of controlled phases: registers are visited in Gray-code order, so the running factor F changes by one
+// multiplication with w_r or its conjugate per step (|w_r| = 1) and only F and the five w_r are live.
+// MJ < 5: the hub is register bit MJ (only registers with that bit set are touched); MJ == 5: all 32.
+template <int MJ>
+__device__ __forceinline__ void apply_ladder(f2 (&a)[kRegs], float fr, float fi, const float (&wr)[kRegBits], const float (&wi)[kRegBits]) {
+    constexpr int NB = (MJ < 5) ? kRegBits - 1 : kRegBits;
+#pragma unroll
+    for (int i = 0; i < (1 << NB); ++i) {
+        const int g = i ^ (i >> 1);
+        if (i) {
+            const int cb = ctz_c(i);
+            const int r = (MJ < 5 && cb >= MJ) ? cb + 1 : cb;
+            const float s = (g >> cb & 1) ? wi[r] : -wi[r];     // entering the bit: * w_r, leaving it: * conj(w_r)
+            const float t = fr * wr[r] - fi * s;
+            fi = fmaf(fr, s, fi * wr[r]);
+            fr = t;
+        }
+        const int k = (MJ < 5) ? ((((g >> MJ) << (MJ + 1)) | (g & ((1 << MJ) - 1))) | (1 << MJ)) : g;
+        const float xr = lo(a[k]), xi = hi(a[k]);
+        a[k] = pk(xr * fr - xi * fi, fmaf(xr, fi, xi * fr));
+    }
+}
+
 // Header of an op.  Each body reloads it for the NEXT op as soon as it has consumed the current
 // values, so the shared-memory latency hides behind the body's FP work and the loop carries no
 // register rotation.
@@ -409,7 +444,6 @@ __device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint3
 #ifndef AQS_TILE_MINB13
 #define AQS_TILE_MINB13 2
 #endif
-__host__ __device__ __forceinline__ constexpr int ctz_c(int i) { return (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : 4; }
 constexpr int tile_min_blocks(int T) { return T >= 13 ? AQS_TILE_MINB13 : AQS_TILE_MINB; }
 
 template <int T>
@@ -524,7 +558,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
             else { if (sub & 1u) apply_factor<K, 10>(a, fr, fi, mask); else apply_factor<K, 9>(a, fr, fi, mask); }    \
         }                                                                                                      \
     } while (0)
-            if (grp < 20u || grp >= 32u) {
+            if (grp < 20u || (grp >= 32u && grp < 42u)) {
                 // shears: grp = kind * 5 + tk (+ 10 with a prescale); 32 + tk: real shears, complex factor on y
                 ShearCoef ka, kb;
                 if (!shear_prelude(op, hd, tid, tile_no, ka, kb)) continue;
@@ -538,6 +572,40 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
                     if (grp < 15u) AQS_SH5(TK_SHR, 1, grp - 10u);
                     else AQS_SH5(TK_SHI, 1, grp - 15u);
                 }
+            } else if (grp == 42u) {
+                // ladder of controlled phases: header, register-control record, n_cont thread/block-control records
+                bool use_b;
+                const bool run = op_predicate(op, word >> 16, hd.h.z, tid, tile_no, use_b);
+                const uint32_t n_cont = hd.h.w;
+                float fr = hd.a.x, fi = hd.a.y;
+                const DevOp* rec = &op + 1;
+                load_head(hd, (&op)[2u + n_cont]);
+                o += 1u + n_cont;
+                if (!run) continue;
+                const float4 w01 = *reinterpret_cast<const float4*>(&rec->a[0]);
+                const float4 w23 = *reinterpret_cast<const float4*>(&rec->b[0]);
+                const float wr[kRegBits] = {w01.x, w01.z, w23.x, w23.z, rec->sx_a};
+                const float wi[kRegBits] = {w01.y, w01.w, w23.y, w23.w, rec->sx_b};
+                for (uint32_t c = 0; c < n_cont; ++c) {
+                    const DevOp& cr = rec[1u + c];
+                    const uint32_t codes = cr.mask;
+                    const float4 ca = *reinterpret_cast<const float4*>(&cr.a[0]);
+                    const float4 cb = *reinterpret_cast<const float4*>(&cr.b[0]);
+                    const float cs[4] = {ca.x, ca.z, cb.x, cb.z}, sn[4] = {ca.y, ca.w, cb.y, cb.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t code = (codes >> (8 * q)) & 0xffu;
+                        const uint32_t src = (code & 0x20u) ? tile_no : tid;
+                        if ((src >> (code & 0x1fu)) & 1u) {
+                            const float t = fr * cs[q] - fi * sn[q];
+                            fi = fmaf(fr, sn[q], fi * cs[q]);
+                            fr = t;
+                        }
+                    }
+                }
+                if (sub & 4u) { if (sub & 1u) apply_ladder<5>(a, fr, fi, wr, wi); else apply_ladder<4>(a, fr, fi, wr, wi); }
+                else if (sub & 2u) { if (sub & 1u) apply_ladder<3>(a, fr, fi, wr, wi); else apply_ladder<2>(a, fr, fi, wr, wi); }
+                else { if (sub & 1u) apply_ladder<1>(a, fr, fi, wr, wi); else apply_ladder<0>(a, fr, fi, wr, wi); }
             } else {
                 bool use_b;
                 const bool run = op_predicate(op, word >> 16, hd.h.z, tid, tile_no, use_b);

@@ -110,11 +110,32 @@ def test_diagonal_gates_ride_inside_the_next_butterfly():
     assert orc.rel_l2(te.run_plan(plan, init), orc.simulate(init.copy(), orc.Circ(n, gates))) < TOL
 
 
+def test_qft_ladders_become_one_op_per_target():
+    """QFT: the CPhase(j, i) of one target merge into a TK_LADDER op whose controls are spread over register,
+    thread and tile-number bits; amplitudes still match the oracle"""
+    for n, x in ((13, 0), (15, 0b101100111010110), (17, 0x1a2b3)):
+        circ = orc.Circ(n, wl.qft(n))
+        plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)
+        ops = []
+        for i in range(plan.info()["n_fused_passes"]):
+            ops += te.parse(plan.export_pass(i))[2]
+        n_ladders = sum(op.kind == te.LADDER for op in ops)
+        n_phase = sum(op.kind in (te.PHASE, te.PHASE_N, te.SCALE_R, te.SCALE_I) for op in ops)
+        assert n_ladders >= n - 4, (n, n_ladders)
+        assert n_phase <= 8, (n, n_phase)                  # the short ladders of the last targets stay plain phases
+        init = orc.new_state(n, x)
+        got = te.run_plan(plan, init)
+        assert orc.rel_l2(got, orc.simulate(init.copy(), circ)) < TOL
+        init = random_state(n, n)
+        assert orc.rel_l2(te.run_plan(plan, init), orc.simulate(init.copy(), circ)) < TOL
+
+
 def test_descriptor_budget_splits_passes():
-    """a 12-qubit state is one tile: 468 gates exceed the per-pass descriptor budget and must split cleanly"""
+    """a 12-qubit state is one tile: 40 QFTs (3120 gates, ~700 descriptors with their controlled-phase ladders
+    merged) exceed the per-pass descriptor budget and must split cleanly"""
     n = 12
     gates = []
-    for _ in range(6):
+    for _ in range(40):
         gates += wl.qft(n)
     circ = orc.Circ(n, gates)
     plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)

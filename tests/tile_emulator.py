@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 K_LANE, K_REG, K_MAX_THREAD_BITS, K_MAX_BITS = 5, 5, 8, 38
-SHR, SHI, GEN, PERM_R, PERM_I, PHASE, SCALE_R, SCALE_I, PHASE_N = range(9)
+SHR, SHI, GEN, PERM_R, PERM_I, PHASE, SCALE_R, SCALE_I, PHASE_N, LADDER, LADDER_CONT = range(11)
 TF_MUX, TF_REGMUX, TF_PRED, TF_PY, TF_IMAG_A, TF_IMAG_B, TF_CY = 1, 2, 4, 8, 16, 32, 64
 
 
@@ -126,6 +126,10 @@ def op_code(kind, tk, mj, flags):
         return ((37 + tk) << 3) | mj
     if kind <= 1:
         return ((kind * 5 + tk + (10 if flags & TF_PY else 0)) << 3) | mj
+    if kind == LADDER:
+        return (42 << 3) | mj
+    if kind == LADDER_CONT:
+        return 63 << 3
     if kind <= 4:
         return ((20 + kind - 2) << 3) | tk
     pat = mj - 1 if mj >= 8 else mj
@@ -205,7 +209,13 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
             stats["resplits"] = stats.get("resplits", 0) + 1
         else:
             assert si == 0, "only the first segment may skip the re-split"
-        for op in ops[sg.first_op: sg.first_op + sg.n_ops]:
+        seg_ops = ops[sg.first_op: sg.first_op + sg.n_ops]
+        skip = 0
+        for oi, op in enumerate(seg_ops):
+            if skip:
+                assert op.kind == LADDER_CONT
+                skip -= 1
+                continue
             mux = bool(op.flags & TF_MUX)
             blk_ok = (blk & np.uint64(op.b_mask)) == np.uint64(op.b_val)                 # (tiles,)
             thr_ok = (tid & np.uint32(op.t_mask)) == np.uint32(op.t_val)                   # (threads,)
@@ -213,6 +223,35 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
             ca, cb = list(op.a), list(op.b)
             assert op.code == (op_code(op.kind, op.tk, op.mj, op.flags) | (op.flags << 16)), "dispatch code does not match (kind, tk, mj, flags)"
             assert bool(op.flags & TF_PRED) == bool(op.t_mask or op.b_mask), "TF_PRED must mirror the predicate fields"
+            if op.kind == LADDER:
+                # header, register-control record, n_cont records of four thread / block controls
+                n_cont = int(np.array([op.sx[0]], dtype=np.float32).view(np.uint32)[0])
+                skip = 1 + n_cont
+                reg = seg_ops[oi + 1]
+                w = [np.complex64(complex(reg.a[2 * r], reg.a[2 * r + 1])) for r in range(4)] + [np.complex64(complex(reg.sx[0], reg.sx[1]))]
+                E = np.full((n_tiles, 1 << TB), np.complex64(complex(op.a[0], op.a[1])), dtype=np.complex64)
+                for c in range(n_cont):
+                    cr = seg_ops[oi + 2 + c]
+                    assert cr.kind == LADDER_CONT
+                    for q in range(4):
+                        code = (cr.mask >> (8 * q)) & 0xff
+                        wq = np.complex64(complex(cr.a[2 * q], cr.a[2 * q + 1]))
+                        if code & 0x20:
+                            bit = ((blk >> np.uint64(code & 0x1f)) & np.uint64(1)).astype(bool)[:, None]
+                        else:
+                            bit = ((tid >> np.uint32(code & 0x1f)) & np.uint32(1)).astype(bool)[None, :]
+                        E = np.where(bit, (E * wq).astype(np.complex64), E)
+                F = np.repeat(E[:, :, None], 32, axis=2)
+                for r in range(5):
+                    on = ((k >> r) & 1).astype(bool)[None, None, :]
+                    F = np.where(on, (F * w[r]).astype(np.complex64), F)
+                sel = factor_mask(op)
+                if op.mj < 5:
+                    assert w[op.mj] == 1, "no control on the hub's own register bit"
+                m = ok[:, :, None] & sel[None, None, :]
+                a = np.where(m, (a * F).astype(np.complex64), a)
+                continue
+            assert op.kind != LADDER_CONT, "stray ladder record"
             if op.kind >= PHASE:
                 assert not mux
                 if op.kind in (PHASE, PHASE_N):
