@@ -17,6 +17,7 @@
 #include "gate_kernels.cuh"
 #include "measure_kernels.cuh"
 #include "peer_kernels.cuh"
+#include "dense_kernels.cuh"
 
 namespace aqs {
 
@@ -646,6 +647,74 @@ int aqs_sample_fixed(aqs_state_t s, const uint64_t* u, uint64_t n, uint64_t* out
 int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     REQUIRE(hist, "null histogram");
     return sample_impl(s, u, nullptr, n, nullptr, hist);
+}
+
+// ---- opaque k-qubit matrices ----------------------------------------------------------
+extern "C++" {
+template <int K>
+static cudaError_t launch_dense(const DenseArgs& A, cudaStream_t st) {
+    const size_t smem = sizeof(float4) << (2 * K);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_dense<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const uint64_t blocks = (A.n_groups + kDenseThreads - 1) / kDenseThreads;
+    k_dense<K><<<(unsigned)blocks, kDenseThreads, smem, st>>>(A);
+    return cudaGetLastError();
+}
+}  // extern "C++"
+
+int aqs_apply_dense(aqs_state_t s, const int* qubits, int k, uint64_t ctrl_mask, uint64_t ctrl_value, const aqs_c32* m) {
+    REQUIRE_INIT();
+    REQUIRE(s && qubits && m, "null argument");
+    REQUIRE(k >= 1 && k <= kDenseMaxK, "dense blocks of 1 to 6 qubits");
+    REQUIRE(k <= s->n, "more target qubits than the state has");
+    const int n = s->n;
+    const int D = 1 << k;
+    DenseArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.a = s->d;
+    uint64_t fixedmask = 0;
+    for (int i = 0; i < k; ++i) {
+        REQUIRE(qubits[i] >= 0 && qubits[i] < n, "target qubit out of range");
+        const int p = n - 1 - qubits[i];
+        REQUIRE(!(fixedmask >> p & 1ull), "duplicate target qubit");
+        fixedmask |= 1ull << p;
+        A.toff[k - 1 - i] = 1ull << p;                  // qubits[0] is the most significant bit of the matrix index
+    }
+    const uint64_t cm = qmask_to_pos(n, ctrl_mask), cv = qmask_to_pos(n, ctrl_value & ctrl_mask);
+    REQUIRE((ctrl_mask >> n) == 0 || n >= 64, "control qubit out of range");
+    REQUIRE(!(cm & fixedmask), "a control qubit is also a target");
+    A.ctrl_or = cv;
+    bitlist_from_mask(fixedmask | cm, A.fixed);
+    A.n_groups = s->N >> A.fixed.n;
+    // matrix -> device as packed operand pairs {re, re, -im, im}
+    std::vector<float> packed((size_t)D * D * 4);
+    for (int i = 0; i < D * D; ++i) {
+        packed[4 * i] = m[i].re; packed[4 * i + 1] = m[i].re;
+        packed[4 * i + 2] = -m[i].im; packed[4 * i + 3] = m[i].im;
+    }
+    const size_t bytes = packed.size() * sizeof(float);
+    int rc = ensure_scratch(s, bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->scratch, packed.data(), bytes, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));          // `packed` is pageable host memory on this frame
+    count_h2d(bytes);
+    A.m = (const float4*)s->scratch;
+    REQUIRE((A.n_groups + kDenseThreads - 1) / kDenseThreads <= 0x7fffffffull, "grid too large");
+    cudaError_t e;
+    switch (k) {
+        case 1: e = launch_dense<1>(A, s->stream); break;
+        case 2: e = launch_dense<2>(A, s->stream); break;
+        case 3: e = launch_dense<3>(A, s->stream); break;
+        case 4: e = launch_dense<4>(A, s->stream); break;
+        case 5: e = launch_dense<5>(A, s->stream); break;
+        default: e = launch_dense<6>(A, s->stream); break;
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "dense kernel launch", __LINE__);
+    count_launch(1);
+    count_ops(1);
+    return AQS_OK;
 }
 
 // ---- peer memory (sharded states on one NVLink / NVSwitch node) ---------------

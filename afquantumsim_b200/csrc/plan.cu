@@ -66,6 +66,7 @@ struct FusedPass {
     std::vector<TileSeg> segs;
     std::vector<TileOp> ops;
     const DevOp* d_ops = nullptr;   // device copy (plan arena), ops.size() + 1 entries
+    bool rare = false;              // some op needs a body that only the full kernel instantiation has (tile_op_is_rare)
 };
 
 }  // namespace aqs
@@ -1131,6 +1132,7 @@ static int plan_variant(int n, int T, const std::vector<POp>& ops, int variant, 
         io_offsets(layouts.back(), fp.st_toff, fp.st_roff);
         fp.scale = make_float2((float)pass_scale.real(), (float)pass_scale.imag());
         fp.has_scale = (pass_scale != cd(1.0, 0.0));
+        for (const TileOp& t : fp.ops) fp.rare = fp.rare || tile_op_is_rare(t.code);
         passes.push_back(std::move(fp));
         cand.swap(rest);
     }
@@ -1238,8 +1240,9 @@ static void fill_params(PassParams& P, float2* state, const FusedPass& fp) {
 static size_t tile_smem_bytes(int T, size_t n_ops) { return (sizeof(float2) << T) + (n_ops + 1) * sizeof(DevOp); }
 
 template <int T>
-static cudaError_t launch_tile(const PassParams& P, uint64_t n_tiles, size_t n_ops, cudaStream_t st) {
-    k_tile2<T><<<(unsigned)n_tiles, 1 << (T - kRegBits), tile_smem_bytes(T, n_ops), st>>>(P);
+static cudaError_t launch_tile(const PassParams& P, uint64_t n_tiles, size_t n_ops, bool rare, cudaStream_t st) {
+    if (rare) k_tile2<T, true><<<(unsigned)n_tiles, 1 << (T - kRegBits), tile_smem_bytes(T, n_ops), st>>>(P);
+    else k_tile2<T, false><<<(unsigned)n_tiles, 1 << (T - kRegBits), tile_smem_bytes(T, n_ops), st>>>(P);
     return cudaGetLastError();
 }
 
@@ -1295,10 +1298,10 @@ static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, cons
     const size_t n_ops = fp.ops.size();
     cudaError_t e;
     switch (fp.T) {
-        case 10: e = launch_tile<10>(P, n_tiles, n_ops, st); break;
-        case 11: e = launch_tile<11>(P, n_tiles, n_ops, st); break;
-        case 12: e = launch_tile<12>(P, n_tiles, n_ops, st); break;
-        default: e = launch_tile<13>(P, n_tiles, n_ops, st); break;
+        case 10: e = launch_tile<10>(P, n_tiles, n_ops, fp.rare, st); break;
+        case 11: e = launch_tile<11>(P, n_tiles, n_ops, fp.rare, st); break;
+        case 12: e = launch_tile<12>(P, n_tiles, n_ops, fp.rare, st); break;
+        default: e = launch_tile<13>(P, n_tiles, n_ops, fp.rare, st); break;
     }
     if (e != cudaSuccess) return fail_cuda(e, "tile kernel launch", __LINE__);
     count_launch(1);
@@ -1307,10 +1310,12 @@ static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, cons
 
 int fused_init() {
     // tile + descriptors exceed the 48 KiB default of dynamic shared memory: opt in once
-    cudaError_t e = cudaFuncSetAttribute(k_tile2<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(10, kOpsLarge));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(11, kOpsLarge));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(12, kOpsLarge));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(13, kOpsLarge));
+    cudaError_t e = cudaSuccess;
+#define AQS_OPT_IN(T)                                                                                                                          \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(T, kOpsLarge)); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile2<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(T, kOpsLarge));
+    AQS_OPT_IN(10) AQS_OPT_IN(11) AQS_OPT_IN(12) AQS_OPT_IN(13)
+#undef AQS_OPT_IN
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tile kernel)", __LINE__);
     return AQS_OK;
 }

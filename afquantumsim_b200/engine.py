@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "aqs_sample", "aqs_sample_fixed", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
     "aqs_state_ipc_export", "aqs_ipc_open", "aqs_ipc_close_all", "aqs_peer_bitswap",
-    "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span",
+    "aqs_apply_dense", "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span",
 ]
 
 
@@ -93,6 +93,7 @@ def load():
         "aqs_counters_get": [P(Counters)], "aqs_counters_reset": [],
         "aqs_state_ipc_export": [vp, vp], "aqs_ipc_open": [vp, P(vp)], "aqs_ipc_close_all": [],
         "aqs_peer_bitswap": [vp, P(vp), i32, P(i32), ctypes.c_uint32],
+        "aqs_apply_dense": [vp, P(i32), i32, u64, u64, vp],
         "aqs_flat_create": [u64, i32, i32, P(vp), P(i32)], "aqs_flat_attach": [vp, i32, i32],
         "aqs_flat_ptr": [vp, P(vp), P(vp)], "aqs_flat_destroy": [vp],
         "aqs_plan_run_shard": [vp, vp, u64, u64, i32, i32], "aqs_plan_pass_span": [vp, u64, i32, P(i32)],
@@ -369,6 +370,15 @@ class State:
     def apply_ops(self, ops: np.ndarray):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         _check(load().aqs_apply_ops(self._h, ops.ctypes.data_as(ctypes.c_void_p), len(ops)))
+
+    def apply_dense(self, qubits: Sequence[int], matrix: np.ndarray, controls: Iterable[int] = (), ctrl_value: Optional[int] = None):
+        """An opaque 2^k x 2^k matrix (row-major, qubits[0] = most significant index bit) on k qubits, k <= 6."""
+        k = len(qubits)
+        m = np.ascontiguousarray(np.asarray(matrix, dtype=np.complex64).reshape(1 << k, 1 << k))
+        q = (ctypes.c_int * k)(*[int(x) for x in qubits])
+        cm = qmask(controls)
+        _check(load().aqs_apply_dense(self._h, q, k, cm, cm if ctrl_value is None else ctrl_value,
+                                      m.ctypes.data_as(ctypes.c_void_p)))
 
     def run(self, plan: Plan):
         _check(load().aqs_plan_run(self._h, plan._h))

@@ -125,6 +125,13 @@ int aqs_sync(aqs_state_t s);
 int aqs_apply_op(aqs_state_t s, const aqs_op* op);
 int aqs_apply_ops(aqs_state_t s, const aqs_op* ops, uint64_t n_ops);
 
+/* An opaque 2^k x 2^k matrix (row-major, m[r * 2^k + c]) on k distinct qubits, 1 <= k <= 6, under the
+ * same control convention as aqs_op: what Gate::operator() / ControlGate::operator() do with a
+ * compiled inner circuit's matrix (src/quantum.cpp:1760-1814, 1888-1950; bit layout src/utils.cpp:137-167),
+ * for arbitrary target qubits.  qubits[0] is the MOST significant bit of the matrix index (inner qubit 0
+ * of the reference's Gate).  One launch, in place, FP32. */
+int aqs_apply_dense(aqs_state_t s, const int* qubits, int k, uint64_t ctrl_mask, uint64_t ctrl_value, const aqs_c32* m);
+
 /* ---- compiled circuits ------------------------------------------------------
  * replaces QCircuit::compile (src/quantum.cpp:199-210): instead of a dense
  * 2^n x 2^n unitary the engine builds a launch plan.  With AQS_PLAN_FUSE the

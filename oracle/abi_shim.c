@@ -193,6 +193,47 @@ int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     free(idx); return AQS_OK;
 }
 
+/* opaque k-qubit matrix on arbitrary qubits: plain loops (the oracle's orc_apply_dense restates the
+ * reference's contiguous Gate / ControlGate embedding; tests compare the two) */
+int aqs_apply_dense(aqs_state_t s, const int* qubits, int k, uint64_t ctrl_mask, uint64_t ctrl_value, const aqs_c32* m) {
+    REQ(s && qubits && m, "null argument");
+    REQ(k >= 1 && k <= 6 && k <= s->n, "dense blocks of 1 to 6 qubits");
+    const int n = s->n, D = 1 << k;
+    uint64_t tmask = 0, toff[6], cm = 0, cv = 0;
+    for (int i = 0; i < k; ++i) {
+        REQ(qubits[i] >= 0 && qubits[i] < n, "target qubit out of range");
+        const uint64_t b = 1ULL << (n - 1 - qubits[i]);
+        REQ(!(tmask & b), "duplicate target qubit");
+        tmask |= b;
+        toff[k - 1 - i] = b;
+    }
+    for (int q = 0; q < n; ++q)
+        if ((ctrl_mask >> q) & 1ULL) { cm |= 1ULL << (n - 1 - q); if ((ctrl_value >> q) & 1ULL) cv |= 1ULL << (n - 1 - q); }
+    REQ(!(cm & tmask), "a control qubit is also a target");
+    c32 in[64];
+    for (uint64_t x = 0; x < s->N; ++x) {
+        if ((x & tmask) || (x & cm) != cv) continue;
+        for (int c = 0; c < D; ++c) {
+            uint64_t off = 0;
+            for (int i = 0; i < k; ++i) if ((c >> i) & 1) off |= toff[i];
+            in[c] = s->a[x | off];
+        }
+        for (int r = 0; r < D; ++r) {
+            float re = 0.f, im = 0.f;
+            for (int c = 0; c < D; ++c) {
+                const aqs_c32 e = m[r * D + c];
+                re += e.re * in[c].re - e.im * in[c].im;
+                im += e.re * in[c].im + e.im * in[c].re;
+            }
+            uint64_t off = 0;
+            for (int i = 0; i < k; ++i) if ((r >> i) & 1) off |= toff[i];
+            s->a[x | off].re = re; s->a[x | off].im = im;
+        }
+    }
+    g_cnt.gate_ops += 1;
+    return AQS_OK;
+}
+
 /* peer memory: there is none across CPU processes.  In-process "members" (plain host pointers)
  * are supported so that tests can check the remap's index arithmetic against a numpy restatement:
  * member `my` performs every swap it shares with a member of higher value. */
