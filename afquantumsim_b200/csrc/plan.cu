@@ -1165,7 +1165,10 @@ static int build_fused(aqs_plan_s* p) {
     std::vector<std::vector<FusedPass>> out(variants);
     std::vector<std::string> errs(variants);
     std::vector<int> rcs(variants, AQS_OK);
-    if (variants == 1) {
+    if (const char* e = std::getenv("AQS_PLAN_ONLY_VARIANT")) {        // dev: run exactly one seeded variant
+        variants = 1;
+        rcs[0] = plan_variant(n, T, ops, std::atoi(e), out[0], errs[0]);
+    } else if (variants == 1) {
         rcs[0] = plan_variant(n, T, ops, 0, out[0], errs[0]);
     } else {
         std::vector<std::thread> workers;

@@ -408,11 +408,13 @@ __device__ __forceinline__ ShearCoef make_coef(bool shi_py, float a, float b, fl
     k.sy = (im && !cy) ? 0.f : sy; k.qy = cy ? qy : (im ? sy : 0.f);
     return k;
 }
+// RARE = false: the lean kernel has no body with an imaginary prescale, so that part of the decode is compiled out
+template <bool RARE>
 __device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint32_t tid, uint32_t tile_no, ShearCoef& ka, ShearCoef& kb) {
     const uint32_t flags = hd.h.x >> 16;
     const bool py = (flags & TF_PY) != 0, cy = (flags & TF_CY) != 0;
     const uint32_t grp = (hd.h.x >> 3) & 0x3fu;
-    const bool shi_py = py && grp >= 15u && grp < 20u;
+    const bool shi_py = RARE && py && grp >= 15u && grp < 20u;
     ka = make_coef(shi_py, hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0, cy, __uint_as_float(hd.h.y));
     kb = ka;
     bool run = true;
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
             if (grp < 20u || (grp >= 32u && grp < 42u)) {
                 // shears: grp = kind * 5 + tk (+ 10 with a prescale); 32 + tk: real shears, complex factor on y
                 ShearCoef ka, kb;
-                if (!shear_prelude(op, hd, tid, tile_no, ka, kb)) continue;
+                if (!shear_prelude<RARE>(op, hd, tid, tile_no, ka, kb)) continue;
                 if (grp >= 32u) {
                     if (grp < 37u) AQS_SH5(TK_SHR, 2, grp - 32u);
                     else AQS_SH5(TK_SHI, 2, grp - 37u);

@@ -431,8 +431,11 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
         "exchange": {"per_step": exchanges, "bytes_per_rank_per_step": xbytes, "peer_memory": remap_p2p or flat_mode, "flat_address_space": flat_mode,
                      "local_passes_per_step": plan_passes, "local_ops_per_step": plan_local_ops,
                      "note": "bytes each rank writes to its peers over NVLink per step (it reads as many)"},
-        "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                     "peak_source": peak_src, "note": "per-GPU kernel roofline is reported by the N=1 run"},
+        "roofline": {"bound": "hbm", "achieved": plan_passes * 2.0 * S_shard / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": plan_passes * 2.0 * S_shard / (ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC_TILE if S_shard == 8.0 * 2 ** 30 else None,
+                     "peak_source": peak_src, "kernel": "fused tile kernel", "launches_per_step": plan_passes,
+                     "note": "per GPU: algorithmic bytes = passes x 2 x shard bytes (every GPU runs 1/N of the tiles of every pass); "
+                             "the kernel is bound by FP32 work and dispatch, and passes whose tiles span GPUs by NVLink (DESIGN.md 3.2, 4)"},
     }
     print(json.dumps(line), flush=True)
     dist.destroy_process_group()
