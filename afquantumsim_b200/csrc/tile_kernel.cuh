@@ -408,25 +408,34 @@ __device__ __forceinline__ ShearCoef make_coef(bool shi_py, float a, float b, fl
     k.sy = (im && !cy) ? 0.f : sy; k.qy = cy ? qy : (im ? sy : 0.f);
     return k;
 }
-// RARE = false: the lean kernel has no body with an imaginary prescale, so that part of the decode is compiled out
+// RARE = false: the lean kernel has no body with an imaginary prescale, so that part of the decode is compiled
+// out and the coefficient sets are taken as stored (the planner writes sx = 1, qy = 0 where a set has none; qy of
+// set a shares its slot with the pair mask, which only the TF_CY bodies read as a float).  Three exits — plain
+// op, register-multiplexed op, predicated op — each with the least work: the prelude is ~40 % of a shear op's
+// instructions.
 template <bool RARE>
 __device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint32_t tid, uint32_t tile_no, ShearCoef& ka, ShearCoef& kb) {
     const uint32_t flags = hd.h.x >> 16;
-    const bool py = (flags & TF_PY) != 0, cy = (flags & TF_CY) != 0;
+    const bool py = (flags & TF_PY) != 0, cy = RARE ? (flags & TF_CY) != 0 : true;
     const uint32_t grp = (hd.h.x >> 3) & 0x3fu;
     const bool shi_py = RARE && py && grp >= 15u && grp < 20u;
     ka = make_coef(shi_py, hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0, cy, __uint_as_float(hd.h.y));
-    kb = ka;
-    bool run = true;
-    if (flags & (TF_PRED | TF_REGMUX)) {
-        const float4 cb = *reinterpret_cast<const float4*>(&op.b[0]);
-        const ShearCoef kset_b = make_coef(shi_py, cb.x, cb.y, cb.z, cb.w, py ? op.sx_b : 1.f, (flags & TF_IMAG_B) != 0, cy, op.qy_b);
-        bool use_b;
-        run = op_predicate(op, flags, hd.h.z, tid, tile_no, use_b);
-        if (use_b) ka = kset_b;
+    if (!(flags & (TF_PRED | TF_REGMUX))) {
         kb = ka;
-        if (flags & TF_REGMUX) kb = kset_b;
+        load_head(hd, (&op)[1]);
+        return true;
     }
+    const float4 cb = *reinterpret_cast<const float4*>(&op.b[0]);
+    const ShearCoef kset_b = make_coef(shi_py, cb.x, cb.y, cb.z, cb.w, (RARE && !py) ? 1.f : op.sx_b, (flags & TF_IMAG_B) != 0, cy, op.qy_b);
+    if (!(flags & TF_PRED)) {
+        kb = kset_b;                     // register-multiplexed: pairs pick their set at compile time
+        load_head(hd, (&op)[1]);
+        return true;
+    }
+    bool use_b;
+    const bool run = op_predicate(op, flags, hd.h.z, tid, tile_no, use_b);
+    if (use_b) ka = kset_b;
+    kb = (flags & TF_REGMUX) ? kset_b : ka;
     load_head(hd, (&op)[1]);
     return run;
 }
