@@ -811,6 +811,10 @@ struct Emitter {
         if (shearing) {
             if (rm == 0) {
                 t.mj = 0;                       // every pair: the kernel uses set a for both subsets
+                for (int i = 0; i < 4; ++i) t.b[i] = t.a[i];     // (and finds a copy of it in set b)
+                t.sx[1] = t.sx[0];
+                t.qy[1] = t.qy[0];
+                if (t.flags & TF_IMAG_A) t.flags |= TF_IMAG_B;
             } else if (popc(rm) == 1 && rv == rm) {
                 t.flags |= TF_REGMUX;           // one control on a register bit: set b = identity leaves the other pairs alone
                 t.mj = (uint8_t)pair_bit(tk, __builtin_ctz(rm));

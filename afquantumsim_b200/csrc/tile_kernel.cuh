@@ -394,7 +394,16 @@ struct OpHead {
     uint4 h;        // {word, mask, tpred, sx_a}
     float4 a;
 };
+#ifndef AQS_HEAD_PREFETCH
+#define AQS_HEAD_PREFETCH 0       // 0: every op loads its own header at the top of the loop; 1: the previous op prefetches it
+                                  // (measured: 161.8 ms against 166.3 ms on brickwork-30 — the prefetch cost eight register copies per op)
+#endif
+__device__ __forceinline__ void load_head_now(OpHead& hd, const DevOp& op) {
+    hd.h = *reinterpret_cast<const uint4*>(&op);
+    hd.a = *reinterpret_cast<const float4*>(&op.a[0]);
+}
 __device__ __forceinline__ void load_head(OpHead& hd, const DevOp& op) {
+    if (!AQS_HEAD_PREFETCH) return;
     hd.h = *reinterpret_cast<const uint4*>(&op);
     hd.a = *reinterpret_cast<const float4*>(&op.a[0]);
 }
@@ -420,7 +429,11 @@ __device__ __forceinline__ bool shear_prelude(const DevOp& op, OpHead& hd, uint3
     const uint32_t grp = (hd.h.x >> 3) & 0x3fu;
     const bool shi_py = RARE && py && grp >= 15u && grp < 20u;
     ka = make_coef(shi_py, hd.a.x, hd.a.y, hd.a.z, hd.a.w, __uint_as_float(hd.h.w), (flags & TF_IMAG_A) != 0, cy, __uint_as_float(hd.h.y));
-    if (!(flags & (TF_PRED | TF_REGMUX))) {
+#ifndef AQS_SETB_ALWAYS
+#define AQS_SETB_ALWAYS 1         // lean kernel: plain ops read set b too (the planner stores a copy of set a there): one exit fewer,
+                                  // no register copies for kb (measured 159.6 ms against 162.6 ms on brickwork-30)
+#endif
+    if (!(AQS_SETB_ALWAYS && !RARE) && !(flags & (TF_PRED | TF_REGMUX))) {
         kb = ka;
         load_head(hd, (&op)[1]);
         return true;
@@ -551,6 +564,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
         load_head(hd, sops[first]);
         for (uint32_t o = first; o < end; ++o) {
             const DevOp& op = sops[o];          // every body leaves the header of op o + 1 in hd (the sentinel keeps it in bounds)
+            if (!AQS_HEAD_PREFETCH) load_head_now(hd, op);
             const uint32_t word = hd.h.x, sub = word & 7u, grp = (word >> 3) & 0x3fu;
 #define AQS_SH(K, TKV, PYV)                                                          \
     do {                                                                             \
