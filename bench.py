@@ -305,7 +305,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": gbs_f, "peak": peak, "unit": "GB/s", "frac": gbs_f / peak,
                      "traffic": NCU_TRAFFIC_TILE if info_f["n_fused_passes"] else NCU_TRAFFIC_PAIR, "peak_source": peak_src,
                      "note": "the fused kernel is bound by FP32 work and interpreter dispatch latency, not HBM "
-                             "(DESIGN.md 3.2: ncu fma pipe 38%, issue 57%); the HBM-bound per-gate kernels are under `unfused.roofline`",
+                             "(DESIGN.md 3.2: ncu fma pipe 40%, issue 56%); the HBM-bound per-gate kernels are under `unfused.roofline`",
                      "kernel": "fused tile kernel" if info_f["n_fused_passes"] else "per-gate kernels",
                      "algorithmic_bytes_per_step": info_f["bytes_planned"], "launches_per_step": info_f["n_launches"]},
         "unfused": {"value": world * gate_apps / (ms_unfused * 1e-3), "unit": "gate-apps/s", "ms_per_step": ms_unfused,
