@@ -1490,6 +1490,22 @@ int aqs_plan_pass_span(aqs_plan_t p, uint64_t index, int log2_world, int* rank_b
     return AQS_OK;
 }
 
+// Introspection (tests): the tiles rank `rank` of 2^log2_world runs in fused pass `index` — the tile numbers whose
+// bits fix_pos[0 .. *fix_n) (ascending) equal those of *fix_or; the launch enumerates the remaining bits.
+int aqs_plan_shard_cut(aqs_plan_t p, uint64_t index, int rank, int log2_world, uint32_t* fix_n, uint32_t* fix_or, uint8_t* fix_pos) {
+    if (!p || !fix_n || !fix_or || !fix_pos) return fail(AQS_ERR_INVALID, "null argument");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    if (log2_world < 0 || log2_world > 6 || rank < 0 || rank >= (1 << log2_world)) return fail(AQS_ERR_INVALID, "bad rank");
+    if (p->n - p->passes[index].T < log2_world) return fail(AQS_ERR_INVALID, "state too small to shard the tiles of a pass");
+    ShardCut cut;
+    int rc = shard_cut(p->n, p->passes[index], rank, log2_world, cut);
+    if (rc) return rc;
+    *fix_n = cut.fix_n;
+    *fix_or = cut.fix_or;
+    std::memcpy(fix_pos, cut.fix_pos, sizeof cut.fix_pos);
+    return AQS_OK;
+}
+
 int aqs_plan_get_info(aqs_plan_t p, aqs_plan_info* info) {
     if (!p || !info) return fail(AQS_ERR_INVALID, "null argument");
     *info = p->info;

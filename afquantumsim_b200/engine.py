@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "aqs_sample", "aqs_sample_fixed", "aqs_sample_hist", "aqs_timer_create", "aqs_timer_start", "aqs_timer_stop",
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
     "aqs_state_ipc_export", "aqs_ipc_open", "aqs_ipc_close_all", "aqs_peer_bitswap",
-    "aqs_apply_dense", "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span",
+    "aqs_apply_dense", "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span", "aqs_plan_shard_cut",
 ]
 
 
@@ -97,6 +97,7 @@ def load():
         "aqs_flat_create": [u64, i32, i32, P(vp), P(i32)], "aqs_flat_attach": [vp, i32, i32],
         "aqs_flat_ptr": [vp, P(vp), P(vp)], "aqs_flat_destroy": [vp],
         "aqs_plan_run_shard": [vp, vp, u64, u64, i32, i32], "aqs_plan_pass_span": [vp, u64, i32, P(i32)],
+        "aqs_plan_shard_cut": [vp, u64, i32, i32, P(ctypes.c_uint32), P(ctypes.c_uint32), P(ctypes.c_uint8)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -231,6 +232,13 @@ class Plan:
         v = ctypes.c_int()
         _check(load().aqs_plan_pass_span(self._h, index, log2_world, ctypes.byref(v)))
         return v.value
+
+    def shard_cut(self, index: int, rank: int, log2_world: int):
+        """(positions, value): rank `rank` runs the tiles of pass `index` whose number has these bits at this value."""
+        n, v = ctypes.c_uint32(), ctypes.c_uint32()
+        pos = (ctypes.c_uint8 * 8)()
+        _check(load().aqs_plan_shard_cut(self._h, index, rank, log2_world, ctypes.byref(n), ctypes.byref(v), pos))
+        return [int(pos[i]) for i in range(n.value)], int(v.value)
 
     def export_pass(self, index: int) -> bytes:
         """Raw launch descriptors of fused pass `index` (tests/tile_emulator.py parses them)."""

@@ -226,6 +226,9 @@ int aqs_flat_ptr(aqs_flat_t f, void** base, void** own_shard);
 int aqs_flat_destroy(aqs_flat_t f);
 int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t first, uint64_t count, int rank, int log2_world);
 int aqs_plan_pass_span(aqs_plan_t p, uint64_t index, int log2_world, int* rank_bits_in_tile);
+/* introspection (tests): which tiles of pass `index` rank `rank` runs — the tile numbers whose bits
+ * fix_pos[0 .. *fix_n) (ascending, 8 entries of storage) equal those of *fix_or */
+int aqs_plan_shard_cut(aqs_plan_t p, uint64_t index, int rank, int log2_world, uint32_t* fix_n, uint32_t* fix_or, uint8_t* fix_pos);
 
 /* ---- timing (CUDA events on the state's stream) ---------------------------- */
 int aqs_timer_create(aqs_timer_t* out);

@@ -263,6 +263,7 @@ int aqs_flat_attach(aqs_flat_t f, int r, int fd) { (void)f; (void)r; (void)fd; r
 int aqs_flat_ptr(aqs_flat_t f, void** b, void** o) { (void)f; (void)b; (void)o; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
 int aqs_flat_destroy(aqs_flat_t f) { (void)f; return AQS_OK; }
 int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t a, uint64_t c, int r, int g) { (void)s; (void)p; (void)a; (void)c; (void)r; (void)g; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
+int aqs_plan_shard_cut(aqs_plan_t p, uint64_t i, int r, int g, uint32_t* n, uint32_t* v, uint8_t* pos) { (void)p; (void)i; (void)r; (void)g; (void)n; (void)v; (void)pos; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
 int aqs_plan_pass_span(aqs_plan_t p, uint64_t i, int g, int* out) { (void)p; (void)i; (void)g; if (out) *out = 0; return AQS_OK; }
 
 int aqs_timer_create(aqs_timer_t* out) { REQ(out, "null"); *out = (aqs_timer_t)calloc(1, sizeof **out); return AQS_OK; }

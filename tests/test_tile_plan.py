@@ -142,3 +142,36 @@ def test_descriptor_budget_splits_passes():
     assert plan.info()["n_fused_passes"] >= 2
     init = random_state(n, 3)
     assert orc.rel_l2(te.run_plan(plan, init), orc.simulate(init.copy(), circ)) < TOL
+
+
+@pytest.mark.parametrize("n,g,seed", [(14, 1, 21), (15, 2, 22), (16, 3, 23)])
+def test_sharded_launches_partition_every_pass(n, g, seed):
+    """Flat multi-GPU address space (aqs_plan_run_shard), on the CPU: the R ranks' launches of a pass touch disjoint
+    tiles whose union is the whole state, a pass without rank bits in its tile stays inside each rank's own shard,
+    and running the ranks one after the other reproduces the unsharded plan bit for bit."""
+    circ = random_circuit(n, 120, seed)
+    plan = eng.Plan(n, lower_array(circ), eng.PLAN_FUSE)
+    P = plan.info()["n_fused_passes"]
+    spans = [plan.pass_span(i, g) for i in range(P)]
+    assert any(spans)
+    init = random_state(n, seed)
+    whole = te.run_plan(plan, init)
+    state = np.array(init, dtype=np.complex64)
+    shard = 1 << (n - g)
+    for i in range(P):
+        raw = plan.export_pass(i)
+        stats = {}
+        for r in np.random.default_rng(seed + i).permutation(1 << g):
+            pos, val = plan.shard_cut(i, int(r), g)
+            assert len(pos) == g
+            te.run_pass(state, raw, stats, cut=(pos, val))
+            touched = stats["touched"][-1]
+            if spans[i] == 0:
+                assert touched.min() >= int(r) * shard and touched.max() < (int(r) + 1) * shard, "a local pass left its shard"
+            else:
+                own = np.count_nonzero((touched >= int(r) * shard) & (touched < (int(r) + 1) * shard))
+                assert own * (1 << spans[i]) == touched.size, "a spanning pass should read 1 / 2^j of its tile from its own shard"
+        allt = np.sort(np.concatenate(stats["touched"]))
+        assert np.array_equal(allt, np.arange(1 << n)), "the ranks' launches do not partition the state"
+    assert np.array_equal(state.view(np.uint32), whole.view(np.uint32))
+    assert orc.rel_l2(state, orc.simulate(init.copy(), circ)) < TOL

@@ -174,8 +174,9 @@ def check_swizzle(seg, T, stats):
         stats["conflicts"] = max(stats.get("conflicts", 0), worst)
 
 
-def run_pass(state: np.ndarray, raw: bytes, stats=None):
-    """apply one exported pass to `state` (complex64, length 2^n) in place"""
+def run_pass(state: np.ndarray, raw: bytes, stats=None, cut=None):
+    """apply one exported pass to `state` (complex64, length 2^n) in place.  cut = (positions, value): a sharded
+    launch (aqs_plan_run_shard) — only the tiles whose number has the bits `positions` equal to those of `value`."""
     stats = stats if stats is not None else {}
     head, segs, ops = parse(raw)
     T = head.tile_bits
@@ -184,6 +185,12 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
     tile_pos = [head.tile.pos[i] for i in range(head.tile.n)]
     assert head.tile.n == T and tile_pos[:5] == [0, 1, 2, 3, 4]
     blk = np.arange(n_tiles, dtype=np.uint64)
+    if cut is not None:
+        # kernel: tile number = blockIdx.x with a zero inserted at every pinned position (ascending), OR value
+        fix_pos, fix_or = cut
+        blk = deposit(np.arange(n_tiles >> len(fix_pos), dtype=np.uint64), fix_pos) | np.uint64(fix_or)
+        n_tiles = blk.size
+        stats.setdefault("touched", []).append(None)
     gbase = deposit(blk, tile_pos)                                       # (tiles,)
     tid = np.arange(1 << TB, dtype=np.uint32)
     k = np.arange(32, dtype=np.uint32)
@@ -194,7 +201,11 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
         return gbase[:, None, None] + g_t[None, :, None] + g_r[None, None, :]
 
     gi = global_index(head.ld_toff, head.ld_roff)
-    assert len(np.unique(gi)) == gi.size == state.size, "entry layout does not cover the state exactly once"
+    if cut is None:
+        assert len(np.unique(gi)) == gi.size == state.size, "entry layout does not cover the state exactly once"
+    else:
+        assert len(np.unique(gi)) == gi.size, "entry layout touches an amplitude twice"
+        stats["touched"][-1] = np.sort(gi.reshape(-1))
     a = state[gi]                                                        # (tiles, threads, 32)
 
     for si, sg in enumerate(segs):
@@ -316,7 +327,10 @@ def run_pass(state: np.ndarray, raw: bytes, stats=None):
                     a[:, :, k1] = np.where(ok, ya, y)
 
     go = global_index(head.st_toff, head.st_roff)
-    assert len(np.unique(go)) == go.size == state.size, "exit layout does not cover the state exactly once"
+    if cut is None:
+        assert len(np.unique(go)) == go.size == state.size, "exit layout does not cover the state exactly once"
+    else:
+        assert np.array_equal(np.sort(go.reshape(-1)), stats["touched"][-1]), "a sharded launch stores where it did not load"
     if head.has_scale:
         a = (a * np.complex64(complex(head.scale[0], head.scale[1]))).astype(np.complex64)
     state[go] = a
