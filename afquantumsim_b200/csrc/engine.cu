@@ -324,7 +324,7 @@ int aqs_engine_device(int* device, int* sms, size_t* hbm) {
     return AQS_OK;
 }
 
-int aqs_state_create(int n, aqs_state_t* out) {
+static int state_alloc(int n, aqs_state_t* out, bool set_zero_state) {
     REQUIRE_INIT();
     REQUIRE(out != nullptr, "null output handle");
     REQUIRE(n >= 1 && n <= AQS_MAX_QUBITS, "qubit count must be in [1, AQS_MAX_QUBITS]");
@@ -341,8 +341,10 @@ int aqs_state_create(int n, aqs_state_t* out) {
     if (e != cudaSuccess) { pool_free(s->d, bytes); delete s; return fail_cuda(e, "cudaStreamCreate", __LINE__); }
     s->own_stream = true;
     *out = s;
-    return aqs_state_set_basis(s, 0);
+    return set_zero_state ? aqs_state_set_basis(s, 0) : AQS_OK;
 }
+
+int aqs_state_create(int n, aqs_state_t* out) { return state_alloc(n, out, true); }
 
 int aqs_state_wrap(int n, void* device_ptr, aqs_state_t* out) {
     REQUIRE_INIT();
@@ -376,10 +378,18 @@ int aqs_state_destroy(aqs_state_t s) {
 int aqs_state_clone(aqs_state_t src, aqs_state_t* out) {
     REQUIRE_INIT();
     REQUIRE(src && out, "null handle");
-    int rc = aqs_state_create(src->n, out);
+    int rc = state_alloc(src->n, out, false);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(src->stream));
-    CUDA_TRY(cudaMemcpyAsync((*out)->d, src->d, src->N * sizeof(float2), cudaMemcpyDeviceToDevice, (*out)->stream));
+    // The copy runs on the SOURCE's stream: it is ordered after everything queued on src, later work on src (and
+    // src's destruction, which synchronises that stream before the buffer returns to the pool) is ordered after it,
+    // and the clone's own stream waits for it through an event.  No host synchronisation.
+    cudaError_t e = cudaMemcpyAsync((*out)->d, src->d, src->N * sizeof(float2), cudaMemcpyDeviceToDevice, src->stream);
+    cudaEvent_t ev = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, src->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((*out)->stream, ev, 0);
+    if (ev) cudaEventDestroy(ev);
+    if (e != cudaSuccess) { aqs_state_destroy(*out); *out = nullptr; return fail_cuda(e, "state clone", __LINE__); }
     return AQS_OK;
 }
 
@@ -598,12 +608,6 @@ static int sample_impl(aqs_state_t s, const float* u_host, const uint64_t* ufix_
     unsigned long long* sums = (unsigned long long*)base;
     float* u_dev = (float*)(base + off_u);
     unsigned long long* out_dev = (unsigned long long*)(base + off_o);
-    uint32_t* hist_dev = nullptr;
-    if (hist_host) {
-        CUDA_TRY(pool_alloc((void**)&hist_dev, s->N * sizeof(uint32_t)));
-        cudaError_t e = cudaMemsetAsync(hist_dev, 0, s->N * sizeof(uint32_t), s->stream);
-        if (e != cudaSuccess) { pool_free(hist_dev, s->N * sizeof(uint32_t)); return fail_cuda(e, "hist memset", __LINE__); }
-    }
     k_tile_sums<<<(unsigned)n_tiles, 256, 0, s->stream>>>(s->d, tile_amps, sums);
     k_scan_tiles<<<1, 1024, 0, s->stream>>>(sums, n_tiles);
     count_launch(2);
@@ -616,7 +620,7 @@ static int sample_impl(aqs_state_t s, const float* u_host, const uint64_t* ufix_
         if (e == cudaSuccess) {
             k_sample<<<(unsigned)n_draws, 256, 0, s->stream>>>(s->d, tile_amps, n_tiles, sums, ufix_host ? nullptr : u_dev,
                                                               ufix_host ? (const unsigned long long*)u_dev : nullptr,
-                                                              out_host ? out_dev : nullptr, hist_dev);
+                                                              out_dev, nullptr);
             count_launch(1);
             e = cudaGetLastError();
         }
@@ -625,14 +629,20 @@ static int sample_impl(aqs_state_t s, const float* u_host, const uint64_t* ufix_
             c_d2h += n_draws * 8;
         }
     }
-    if (e == cudaSuccess && hist_host) {
-        e = cudaMemcpyAsync(hist_host, hist_dev, s->N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
-        c_d2h += s->N * sizeof(uint32_t);
-    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     else cudaStreamSynchronize(s->stream);
-    if (hist_dev) pool_free(hist_dev, s->N * sizeof(uint32_t));
     if (e != cudaSuccess) return fail_cuda(e, "sampling", __LINE__);
+    return AQS_OK;
+}
+
+// Histograms are built on the HOST from the n outcome indices (8 bytes per draw come back from the device, not a
+// dense uint32[2^n]: 4 GiB at n = 30 for 1000 draws).  Sorted (index, count) pairs first; the dense vector of the
+// reference's return type (src/quantum.cpp:467-501) is filled from them.
+static int sample_sorted(aqs_state_t s, const float* u, uint64_t n, std::vector<uint64_t>& out) {
+    out.resize(n);
+    int rc = sample_impl(s, u, nullptr, n, out.data(), nullptr);
+    if (rc) return rc;
+    std::sort(out.begin(), out.end());
     return AQS_OK;
 }
 
@@ -645,8 +655,38 @@ int aqs_sample_fixed(aqs_state_t s, const uint64_t* u, uint64_t n, uint64_t* out
     return sample_impl(s, nullptr, u, n, out, nullptr);
 }
 int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
-    REQUIRE(hist, "null histogram");
-    return sample_impl(s, u, nullptr, n, nullptr, hist);
+    REQUIRE(s && hist, "null argument");
+    REQUIRE(u || n == 0, "null draws");
+    std::vector<uint64_t> idx;
+    int rc = sample_sorted(s, u, n, idx);
+    if (rc) return rc;
+    std::memset(hist, 0, s->N * sizeof(uint32_t));
+    for (uint64_t k : idx) ++hist[k];
+    return AQS_OK;
+}
+int aqs_sample_hist_sparse(aqs_state_t s, const float* u, uint64_t n, uint64_t* index, uint32_t* count, uint64_t cap, uint64_t* n_bins) {
+    REQUIRE(s && n_bins, "null argument");
+    REQUIRE(u || n == 0, "null draws");
+    std::vector<uint64_t> idx;
+    int rc = sample_sorted(s, u, n, idx);
+    if (rc) return rc;
+    uint64_t bins = 0;
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i;
+        while (j < n && idx[j] == idx[i]) ++j;
+        if (index && count && bins < cap) { index[bins] = idx[i]; count[bins] = (uint32_t)(j - i); }
+        ++bins;
+        i = j;
+    }
+    *n_bins = bins;
+    if (index && count && bins > cap) return fail(AQS_ERR_INVALID, "histogram has more bins than the output arrays hold");
+    return AQS_OK;
+}
+int aqs_pool_trim(void) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& pe : g_pool) cudaFree(pe.p);
+    g_pool.clear();
+    return AQS_OK;
 }
 
 // ---- opaque k-qubit matrices ----------------------------------------------------------

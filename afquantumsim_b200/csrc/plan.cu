@@ -32,8 +32,7 @@
 #include <thread>
 #include <vector>
 
-#include "engine_internal.h"
-#include "tile_kernel.cuh"
+#include "plan_internal.h"
 
 namespace aqs {
 
@@ -56,34 +55,7 @@ struct POp {
     cd gs = cd(1, 0);        // scalar that came with it (diag(d0, d1) = d0 * diag(1, d1/d0)): goes to the pass-wide scale
 };
 
-struct FusedPass {
-    int T = 0;
-    uint64_t n_tiles = 0;
-    float2 scale = make_float2(1.f, 0.f);
-    bool has_scale = false;
-    BitList tile;
-    uint64_t ld_toff[kMaxThreadBits], ld_roff[kRegBits], st_toff[kMaxThreadBits], st_roff[kRegBits];
-    std::vector<TileSeg> segs;
-    std::vector<TileOp> ops;
-    const DevOp* d_ops = nullptr;   // device copy (plan arena), ops.size() + 1 entries
-    bool rare = false;              // some op needs a body that only the full kernel instantiation has (tile_op_is_rare)
-};
-
 }  // namespace aqs
-
-struct aqs_plan_s {
-    int n = 0;
-    uint32_t flags = 0;
-    std::vector<aqs::CanonOp> ops;       // per-gate path
-    std::vector<aqs::FusedPass> passes;  // fused path (empty => run ops one by one)
-    void* arena = nullptr;               // device copy of every pass's DevOps
-    size_t arena_bytes = 0;
-    cudaGraphExec_t graph = nullptr;     // AQS_PLAN_GRAPH: the launch sequence captured for `graph_state`
-    const void* graph_state = nullptr;
-    cudaStream_t last_stream = nullptr;  // stream of the most recent run (synchronised before the arena is recycled)
-    bool ran = false;
-    aqs_plan_info info{};
-};
 
 namespace aqs {
 
@@ -1302,6 +1274,12 @@ static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, cons
         std::memcpy(P.fix_pos, cut->fix_pos, sizeof P.fix_pos);
         n_tiles >>= cut->fix_n;
     }
+    if (fp.spec && spec_ready(fp)) {
+        int rc = spec_launch(fp, state, n_tiles, P.fix_n, P.fix_or, P.fix_pos, st);
+        if (rc) return rc;
+        count_launch(1);
+        return AQS_OK;
+    }
     const size_t n_ops = fp.ops.size();
     cudaError_t e;
     switch (fp.T) {
@@ -1358,6 +1336,15 @@ int aqs_plan_build(int n, const aqs_op* ops, uint64_t n_ops, uint32_t flags, aqs
         if (rc) { aqs_plan_destroy(p); return rc; }
     }
     if (!p->passes.empty()) {
+        // AQS_JIT=0 turns specialisation off, AQS_JIT=1 forces it (waiting), AQS_JIT=2 forces it in the background
+        uint32_t jit = flags & (AQS_PLAN_JIT | AQS_PLAN_JIT_ASYNC);
+        if (const char* e = std::getenv("AQS_JIT")) jit = (*e == '0') ? 0u : (*e == '2' ? AQS_PLAN_JIT_ASYNC : AQS_PLAN_JIT);
+        size_t max_passes = 256;           // huge plans (Grover-26: thousands of passes) only pay when shapes repeat
+        if (const char* e = std::getenv("AQS_JIT_MAX_PASSES")) max_passes = (size_t)std::max(0, std::atoi(e));
+        if (jit && p->passes.size() <= max_passes) {
+            p->spec_requested = true;
+            spec_attach(n, p->passes, (jit & AQS_PLAN_JIT) != 0);
+        }
         p->info.n_launches = p->passes.size();
         p->info.n_fused_passes = p->passes.size();
         p->info.n_single_ops = 0;
@@ -1420,7 +1407,6 @@ int aqs_plan_run(aqs_state_t s, aqs_plan_t p) {
     if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
     int up = ensure_uploaded(p);
     if (up) return up;
-    p->last_stream = s->stream;
     p->ran = true;
     if (p->flags & AQS_PLAN_GRAPH) {
         // launch-bound plans (small states, thousands of passes): replay one CUDA graph instead of
@@ -1465,7 +1451,6 @@ int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t first, uint64_t cou
     if (p->n - p->passes[0].T < log2_world) return fail(AQS_ERR_INVALID, "state too small to shard the tiles of a pass");
     int up = ensure_uploaded(p);
     if (up) return up;
-    p->last_stream = s->stream;
     p->ran = true;
     for (uint64_t i = first; i < first + count; ++i) {
         ShardCut cut;
@@ -1543,9 +1528,51 @@ int aqs_plan_export_pass(aqs_plan_t p, uint64_t index, void* buf, uint64_t cap, 
     return AQS_OK;
 }
 
+int aqs_plan_pass_source(aqs_plan_t p, uint64_t index, char* buf, uint64_t cap, uint64_t* needed, uint64_t* geom) {
+    if (!p || !needed) return fail(AQS_ERR_INVALID, "null argument");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    SpecSource s;
+    std::string why;
+    if (!spec_generate(p->n, p->passes[index], s, why)) return fail(AQS_ERR_STATE, "pass cannot be specialised: " + why);
+    *needed = s.src.size() + 1;
+    if (geom) { geom[0] = (uint64_t)s.threads; geom[1] = s.smem_bytes; geom[2] = p->passes[index].n_tiles; }
+    if (buf && cap >= s.src.size() + 1) std::memcpy(buf, s.src.c_str(), s.src.size() + 1);
+    return AQS_OK;
+}
+
+int aqs_plan_pass_coefs(aqs_plan_t p, uint64_t index, uint64_t* buf, uint64_t cap, uint64_t* needed) {
+    if (!p || !needed) return fail(AQS_ERR_INVALID, "null argument");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    SpecSource s;
+    std::string why;
+    if (!spec_generate(p->n, p->passes[index], s, why)) return fail(AQS_ERR_STATE, "pass cannot be specialised: " + why);
+    *needed = s.coefs.size();
+    if (buf && cap >= s.coefs.size()) std::memcpy(buf, s.coefs.data(), s.coefs.size() * sizeof(uint64_t));
+    return AQS_OK;
+}
+
+int aqs_plan_jit_ready(aqs_plan_t p, uint64_t* n_ready) {
+    if (!p || !n_ready) return fail(AQS_ERR_INVALID, "null argument");
+    uint64_t c = 0;
+    for (const FusedPass& fp : p->passes) c += (fp.spec && spec_ready(fp)) ? 1 : 0;
+    *n_ready = c;
+    return AQS_OK;
+}
+
+int aqs_jit_wait(void) { return spec_wait_all(); }
+
+int aqs_jit_get_info(aqs_jit_info* out) {
+    if (!out) return fail(AQS_ERR_INVALID, "null argument");
+    spec_stats(&out->compiled, &out->cache_hits, &out->failed, &out->compile_seconds, &out->pending);
+    return AQS_OK;
+}
+
 int aqs_plan_destroy(aqs_plan_t p) {
     if (!p) return AQS_OK;
-    if (p->ran && p->arena && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();   // kernels may still read the arena
+    // The plan may have run on several streams (a cached QCircuit plan is shared by every QSimulator, each with its own
+    // non-blocking stream), some of them caller-owned or already destroyed: wait for the whole device before the
+    // descriptor arena goes back to the pool, where the next plan would overwrite it under kernels still reading it.
+    if (p->ran && p->arena && cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();
     if (p->graph) cudaGraphExecDestroy(p->graph);
     if (p->arena) pool_free(p->arena, p->arena_bytes);
     delete p;

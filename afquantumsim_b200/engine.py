@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AQS_ENGINE_LIB") or os.path.join(_HERE, "lib", "libaqs_engine.so")   # the override is for A/B builds of the engine
 
 OP_U2, OP_DIAG, OP_X, OP_SWAP = 0, 1, 2, 3
-PLAN_FUSE, PLAN_GRAPH = 1, 2
+PLAN_FUSE, PLAN_GRAPH, PLAN_JIT, PLAN_JIT_ASYNC = 1, 2, 4, 8
 
 # struct aqs_op (64 bytes) as a numpy record, so op lists are one contiguous buffer
 OP_DTYPE = np.dtype([
@@ -39,6 +39,11 @@ class Counters(ctypes.Structure):
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
 
 
+class JitInfo(ctypes.Structure):
+    _fields_ = [("compiled", ctypes.c_uint64), ("cache_hits", ctypes.c_uint64), ("failed", ctypes.c_uint64),
+                ("pending", ctypes.c_uint64), ("compile_seconds", ctypes.c_double)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -58,6 +63,7 @@ ABI_SYMBOLS = [
     "aqs_timer_elapsed_ms", "aqs_timer_destroy", "aqs_counters_get", "aqs_counters_reset",
     "aqs_state_ipc_export", "aqs_ipc_open", "aqs_ipc_close_all", "aqs_peer_bitswap",
     "aqs_apply_dense", "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span", "aqs_plan_shard_cut",
+    "aqs_plan_pass_source", "aqs_plan_pass_coefs", "aqs_plan_jit_ready", "aqs_jit_wait", "aqs_jit_get_info",
 ]
 
 
@@ -98,6 +104,8 @@ def load():
         "aqs_flat_ptr": [vp, P(vp), P(vp)], "aqs_flat_destroy": [vp],
         "aqs_plan_run_shard": [vp, vp, u64, u64, i32, i32], "aqs_plan_pass_span": [vp, u64, i32, P(i32)],
         "aqs_plan_shard_cut": [vp, u64, i32, i32, P(ctypes.c_uint32), P(ctypes.c_uint32), P(ctypes.c_uint8)],
+        "aqs_plan_pass_source": [vp, u64, vp, u64, P(u64), P(u64)], "aqs_plan_pass_coefs": [vp, u64, vp, u64, P(u64)],
+        "aqs_plan_jit_ready": [vp, P(u64)], "aqs_jit_wait": [], "aqs_jit_get_info": [P(JitInfo)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -248,6 +256,24 @@ class Plan:
         _check(load().aqs_plan_export_pass(self._h, index, buf, need.value, ctypes.byref(need)))
         return buf.raw
 
+    def pass_source(self, index: int):
+        """(source, coefs, threads, smem_bytes, n_ctas) of the specialised kernel of fused pass `index` (specialize.cu)."""
+        need = ctypes.c_uint64()
+        geom = (ctypes.c_uint64 * 3)()
+        _check(load().aqs_plan_pass_source(self._h, index, None, 0, ctypes.byref(need), geom))
+        buf = ctypes.create_string_buffer(need.value)
+        _check(load().aqs_plan_pass_source(self._h, index, buf, need.value, ctypes.byref(need), geom))
+        _check(load().aqs_plan_pass_coefs(self._h, index, None, 0, ctypes.byref(need)))
+        coefs = np.zeros(need.value, dtype=np.uint64)
+        _check(load().aqs_plan_pass_coefs(self._h, index, coefs.ctypes.data_as(ctypes.c_void_p), need.value, ctypes.byref(need)))
+        return buf.value.decode(), coefs, int(geom[0]), int(geom[1]), int(geom[2])
+
+    def jit_ready(self) -> int:
+        """Number of fused passes that would run on their specialised kernel if the plan ran now."""
+        v = ctypes.c_uint64()
+        _check(load().aqs_plan_jit_ready(self._h, ctypes.byref(v)))
+        return int(v.value)
+
     def close(self):
         if self._h:
             load().aqs_plan_destroy(self._h)
@@ -258,6 +284,17 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def jit_wait() -> None:
+    """Block until every queued specialisation has been compiled."""
+    _check(load().aqs_jit_wait())
+
+
+def jit_info() -> dict:
+    ji = JitInfo()
+    _check(load().aqs_jit_get_info(ctypes.byref(ji)))
+    return {k: getattr(ji, k) for k, _ in JitInfo._fields_}
 
 
 class Timer:

@@ -139,6 +139,12 @@ int aqs_apply_dense(aqs_state_t s, const int* qubits, int k, uint64_t ctrl_mask,
  * shared memory and apply the whole group in place. */
 #define AQS_PLAN_FUSE  1u   /* gate-fusion pass on */
 #define AQS_PLAN_GRAPH 2u   /* capture the launch sequence in a CUDA graph */
+#define AQS_PLAN_JIT   4u   /* (with AQS_PLAN_FUSE) specialise every fused pass: a straight-line sm_100a kernel per pass
+                             * SHAPE, compiled at run time and cached by shape for the life of the process; the
+                             * coefficients stay kernel parameters, so circuits that differ only in their angles
+                             * share kernels.  aqs_plan_build returns when the kernels are compiled. */
+#define AQS_PLAN_JIT_ASYNC 8u /* same, but compilation runs on background host threads: a pass runs on the generic
+                             * (interpreting) tile kernel until its specialised kernel is ready */
 typedef struct aqs_plan_info {
     uint64_t n_ops;            /* primitive ops (= gate applications) */
     uint64_t n_launches;       /* kernel launches per run */
@@ -157,6 +163,24 @@ int aqs_plan_destroy(aqs_plan_t p);
  * kernel receives them (record layout: afquantumsim_b200/csrc/plan.cu).  *needed gets the record
  * size; the record is copied when cap is large enough.  No reference counterpart. */
 int aqs_plan_export_pass(aqs_plan_t p, uint64_t index, void* buf, uint64_t cap, uint64_t* needed);
+/* Specialised passes (afquantumsim_b200/csrc/specialize.cu; no reference counterpart: QCircuit::compile's product is
+ * a dense matrix, src/quantum.cpp:199-210).  aqs_plan_pass_source: the generated CUDA C++ of fused pass `index`
+ * (also valid host C++ under -DAQS_HOST_EMU, which is how the CPU tests execute it) and aqs_plan_pass_coefs: its
+ * table of packed 64-bit coefficient operands; both work without a GPU and without AQS_PLAN_JIT.  *geom gets
+ * {threads per CTA, dynamic shared-memory bytes, CTAs of a full launch}.  aqs_plan_jit_ready: how many fused passes
+ * of the plan would run specialised if the plan ran now.  aqs_jit_wait blocks until no compilation is pending. */
+int aqs_plan_pass_source(aqs_plan_t p, uint64_t index, char* buf, uint64_t cap, uint64_t* needed, uint64_t* geom);
+int aqs_plan_pass_coefs(aqs_plan_t p, uint64_t index, uint64_t* buf, uint64_t cap, uint64_t* needed);
+int aqs_plan_jit_ready(aqs_plan_t p, uint64_t* n_ready);
+int aqs_jit_wait(void);
+typedef struct aqs_jit_info {
+    uint64_t compiled;         /* kernels compiled by this process */
+    uint64_t cache_hits;       /* passes that found their shape already compiled (or compiling) */
+    uint64_t failed;           /* compilations that failed (those passes stay on the generic kernel) */
+    uint64_t pending;          /* compilations queued or running */
+    double   compile_seconds;  /* host-thread seconds spent compiling (summed over threads) */
+} aqs_jit_info;
+int aqs_jit_get_info(aqs_jit_info* out);
 
 /* ---- probabilities and measurement -----------------------------------------
  * Exact-sum contract: p_k = fl32(fl32(re*re)+fl32(im*im)),
