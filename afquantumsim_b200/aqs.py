@@ -99,6 +99,16 @@ def set_fusion(on: bool) -> None:
     _load().aqsh_set_fusion(1 if on else 0)
 
 
+def set_jit_min_qubits(n: int) -> None:
+    """Specialised pass kernels are requested for circuits on at least n qubits (default 26)."""
+    _load().aqsh_set_jit_min_qubits(int(n))
+
+
+def jit_wait() -> None:
+    """Block until no kernel compilation is pending."""
+    _load().aqsh_jit_wait()
+
+
 def get_fusion() -> bool:
     return bool(_load().aqsh_get_fusion())
 

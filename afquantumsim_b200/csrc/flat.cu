@@ -138,10 +138,16 @@ int aqs_flat_create(uint64_t shard_bytes, int world, int rank, aqs_flat_t* out, 
     f->mapped.assign(world, 0);
     CUmemGenericAllocationHandle h = 0;
     CUresult r = g_drv.MemCreate(&h, f->shard_bytes, &prop, 0);
+    if (r == CUDA_ERROR_OUT_OF_MEMORY) {
+        // cuMemCreate does not see the engine's cache of recycled state buffers: give them back and retry once
+        aqs_pool_trim();
+        r = g_drv.MemCreate(&h, f->shard_bytes, &prop, 0);
+    }
     if (r != CUDA_SUCCESS) { delete f; return r == CUDA_ERROR_OUT_OF_MEMORY ? aqs::fail(AQS_ERR_NOMEM, "cuMemCreate: out of device memory") : fail_drv(r, "cuMemCreate"); }
     r = g_drv.MemAddressReserve(&f->base, f->shard_bytes * (size_t)world, f->shard_bytes < (1ull << 21) ? 0 : (1ull << 21), 0, 0);
     if (r != CUDA_SUCCESS) { g_drv.MemRelease(h); delete f; return fail_drv(r, "cuMemAddressReserve"); }
     int rc = map_slot(f, rank, h);
+    if (rc != AQS_OK && !f->handles[rank]) g_drv.MemRelease(h);      // cuMemMap failed before the handle was recorded
     if (rc == AQS_OK) {
         r = g_drv.MemExportToShareableHandle(&f->own_fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
         if (r != CUDA_SUCCESS) rc = fail_drv(r, "cuMemExportToShareableHandle");
@@ -158,7 +164,7 @@ int aqs_flat_attach(aqs_flat_t f, int peer_rank, int fd) {
     CUmemGenericAllocationHandle h = 0;
     DRV_TRY(g_drv.MemImportFromShareableHandle(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
     int rc = map_slot(f, peer_rank, h);
-    if (rc != AQS_OK && !f->mapped[peer_rank]) g_drv.MemRelease(h);
+    if (rc != AQS_OK && !f->handles[peer_rank]) g_drv.MemRelease(h);   // (a recorded handle is released by aqs_flat_destroy)
     return rc;
 }
 

@@ -1121,7 +1121,7 @@ static int plan_variant(int n, int T, const std::vector<POp>& ops, int variant, 
 // and the choice does not depend on thread timing, so every rank of a sharded run builds the same plan.
 static int build_fused(aqs_plan_s* p) {
     const int n = p->n;
-    int T = std::min(n, 12);
+    int T = std::min(n, 13);      // 8192 amplitudes per tile: fewer passes (brickwork-30: 15 instead of 21); specialised kernels 63.7 ms against 68.6 at T = 12, the generic kernel 153 against 159.5
     if (const char* e = std::getenv("AQS_TILE_BITS")) {
         const int t = std::atoi(e);
         if (t >= kMinTileBits && t <= kMaxTileBits) T = std::min(n, t);
@@ -1339,7 +1339,7 @@ int aqs_plan_build(int n, const aqs_op* ops, uint64_t n_ops, uint32_t flags, aqs
         // AQS_JIT=0 turns specialisation off, AQS_JIT=1 forces it (waiting), AQS_JIT=2 forces it in the background
         uint32_t jit = flags & (AQS_PLAN_JIT | AQS_PLAN_JIT_ASYNC);
         if (const char* e = std::getenv("AQS_JIT")) jit = (*e == '0') ? 0u : (*e == '2' ? AQS_PLAN_JIT_ASYNC : AQS_PLAN_JIT);
-        size_t max_passes = 256;           // huge plans (Grover-26: thousands of passes) only pay when shapes repeat
+        size_t max_passes = 8192;          // (source generation is ~0.2 ms per pass; spec_attach bounds the number of NEW kernels)
         if (const char* e = std::getenv("AQS_JIT_MAX_PASSES")) max_passes = (size_t)std::max(0, std::atoi(e));
         if (jit && p->passes.size() <= max_passes) {
             p->spec_requested = true;

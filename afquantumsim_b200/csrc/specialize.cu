@@ -26,8 +26,11 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
+#include <complex>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -118,9 +121,14 @@ struct Gen {
         o += big.data();
     }
     std::string R(int k) const { return "a" + std::to_string(phys[k]); }
+    std::unordered_map<uint64_t, size_t> coef_index;
     std::string C(uint64_t bits) {
-        coefs.push_back(bits);
-        return "c" + std::to_string(coefs.size() - 1);
+        auto it = coef_index.find(bits);
+        if (it == coef_index.end()) {
+            coefs.push_back(bits);
+            it = coef_index.emplace(bits, coefs.size() - 1).first;
+        }
+        return "c" + std::to_string(it->second);
     }
     std::string BC(float v) { return C(pack2(v, v)); }         // (v, v): real factor
     std::string IM(float v) { return C(pack2(-v, v)); }        // (-v, v): with sw(): multiplication by i*v
@@ -141,6 +149,86 @@ struct Gen {
         return e;
     }
 
+    // ---- deferred scales ---------------------------------------------------------------------------
+    // The true value of a register is  sc * stored,  sc = re * i^p  (re > 0, p mod 4), tracked while the source is
+    // written.  Every op is linear, so real and imaginary factors — the prescales of reflections (CX folded into a
+    // rotation), signs, X / Y / Z-like factors, and the cosine that a rotation has in common on both outputs — are
+    // never multiplied into the data: they are folded into the coefficients of the next op that combines two
+    // registers.  A rotation is then TWO packed FMAs per amplitude pair,
+    //     x' = c (x - t y),  y' = c (y + t x)      (or the anti-diagonal form when |sin| > |cos|),
+    // instead of three shears, and a general SU(2) (diagonal gate folded in) four.  Scales are materialised
+    // (one FMUL2 per register that differs from the majority) only where the pattern would stop being a function of
+    // the register index alone — before a layout change, before an op under a run-time predicate — and the common
+    // factor goes to the final store.
+    struct Sc {
+        double re = 1.0;
+        int p = 0;
+    };
+    static Sc mk(double re, int p) {
+        Sc z;
+        z.re = re;
+        z.p = p & 3;
+        if (z.re < 0) { z.re = -z.re; z.p = (z.p + 2) & 3; }
+        return z;
+    }
+    static Sc sc_mul(Sc a, Sc b) { return mk(a.re * b.re, a.p + b.p); }
+    static Sc sc_div(Sc a, Sc b) { return mk(a.re / b.re, a.p - b.p + 4); }
+    static bool is0(Sc a) { return a.re == 0.0; }
+    static bool is1(Sc a) { return a.p == 0 && std::fabs(a.re - 1.0) <= 1e-13; }
+    static bool sc_eq(Sc a, Sc b) { return a.p == b.p && std::fabs(a.re - b.re) <= 1e-12 * std::max(a.re, b.re); }
+    static std::complex<double> sc_val(Sc a) {
+        static const std::complex<double> ip[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+        return a.re * ip[a.p];
+    }
+    Sc sc[kRegs];                             // indexed by PHYSICAL variable
+    std::complex<double> gscale{1.0, 0.0};    // common factor of every amplitude of the tile, applied at the final store
+
+    // coefficient operand for  k * r  as one packed multiply / FMA operand pair: (coef, operand expression)
+    std::string coef_of(Sc k) {
+        switch (k.p) {
+            case 0: return BC((float)k.re);
+            case 2: return BC((float)-k.re);
+            case 1: return IM((float)k.re);
+            default: return IM((float)-k.re);
+        }
+    }
+    static std::string opnd_of(Sc k, const std::string& r) { return (k.p & 1) ? "sw(" + r + ")" : r; }
+    std::string V(int v) const { return "a" + std::to_string(v); }
+
+    void rescale_var(int v, Sc target) {
+        const Sc r = sc_div(sc[v], target);
+        if (!is1(r)) {
+            const std::string c = coef_of(r);
+            P("  a%d = mul2(%s, %s);\n", v, c.c_str(), opnd_of(r, V(v)).c_str());
+        }
+        sc[v] = target;
+    }
+    Sc majority(const std::vector<int>& vars) const {
+        Sc best = sc[vars[0]];
+        int best_n = 0;
+        for (int v : vars) {
+            int c = 0;
+            for (int w : vars) c += sc_eq(sc[v], sc[w]);
+            if (c > best_n) { best_n = c; best = sc[v]; }
+        }
+        return best;
+    }
+    // give the listed variables one common scale (which commutes with any linear op on them)
+    void equalize(const std::vector<int>& vars) {
+        if (vars.empty()) return;
+        const Sc m = majority(vars);
+        for (int v : vars) rescale_var(v, m);
+    }
+    // before a layout change / the final store: every register to the majority scale, which becomes global
+    void materialize_all() {
+        std::vector<int> all(kRegs);
+        for (int k = 0; k < kRegs; ++k) all[k] = k;
+        const Sc m = majority(all);
+        for (int v : all) rescale_var(v, m);
+        gscale *= sc_val(m);
+        for (int v : all) sc[v] = Sc();
+    }
+
     // ---- shears -------------------------------------------------------------------------------
     struct ShearSet {
         float a, b, g, sx, sy, qy;
@@ -149,6 +237,88 @@ struct Gen {
         // same instruction sequence for both sets (so that a per-thread select of the coefficients suffices)?
         bool same_form(const ShearSet& z) const { return py == z.py && cy == z.cy && imag == z.imag; }
     };
+    static void pair_regs(int tk, int p, int& k0, int& k1) {
+        k0 = ((p >> tk) << (tk + 1)) | (p & ((1 << tk) - 1));
+        k1 = k0 | (1 << tk);
+    }
+
+    // -- fast form: M = N(a, b, g) * diag(px, py) on a pair whose registers carry deferred scales sx0, sy0
+    struct Fast {
+        bool need_f = false;             // the factor on y is a general complex number: multiplied in explicitly
+        std::complex<double> f{1, 0};
+        bool anti = false;               // pivot on the anti-diagonal: the outputs land in each other's variables
+        Sc k1, k2;                       // A += k1 * B_old,  B += k2 * A_old   (A, B = x, y variables; swapped when anti)
+        Sc ox, oy;                       // deferred scales of the new logical x / y
+    };
+    static Fast fast_form(const ShearSet& s, bool shi, Sc sx0, Sc sy0) {
+        Fast F;
+        Sc fx = Sc(), fy = Sc();
+        if (s.py) {
+            fx = s.imag ? mk(s.sx, 1) : mk(s.sx, 0);
+            if (s.cy) {
+                if (s.qy == 0.f) fy = mk(s.sy, 0);
+                else if (s.sy == 0.f) fy = mk(s.qy, 1);
+                else { F.need_f = true; F.f = std::complex<double>(s.sy, s.qy); }
+            } else {
+                fy = s.imag ? mk(s.sy, 1) : mk(s.sy, 0);
+            }
+        }
+        const double a = s.a, b = s.b, g = s.g;
+        Sc n00, n01, n10, n11;
+        if (!shi) { n00 = mk(1 + a * b, 0); n01 = mk(a + g + a * b * g, 0); n10 = mk(b, 0); n11 = mk(1 + b * g, 0); }
+        else { n00 = mk(1 - a * b, 0); n01 = mk(a + g - a * b * g, 1); n10 = mk(b, 1); n11 = mk(1 - b * g, 0); }
+        const Sc ex = sc_mul(sx0, fx), ey = sc_mul(sy0, fy);
+        const Sc E00 = sc_mul(n00, ex), E01 = sc_mul(n01, ey), E10 = sc_mul(n10, ex), E11 = sc_mul(n11, ey);
+        if (E00.re * E11.re >= E01.re * E10.re) {
+            F.anti = false;
+            F.k1 = is0(E01) ? E01 : sc_div(E01, E00);
+            F.k2 = is0(E10) ? E10 : sc_div(E10, E11);
+            F.ox = E00; F.oy = E11;
+        } else {
+            // x' = E01 (y + (E00/E01) x),  y' = E10 (x + (E11/E10) y)
+            F.anti = true;
+            F.k1 = is0(E00) ? E00 : sc_div(E00, E01);
+            F.k2 = is0(E11) ? E11 : sc_div(E11, E10);
+            F.ox = E01; F.oy = E10;
+        }
+        return F;
+    }
+    struct FastNames { std::string fr, fi, c1, c2; };
+    FastNames fast_names(const Fast& F) {
+        FastNames nm;
+        if (F.need_f) { nm.fr = BC((float)F.f.real()); nm.fi = IM((float)F.f.imag()); }
+        if (!is0(F.k1)) nm.c1 = coef_of(F.k1);
+        if (!is0(F.k2)) nm.c2 = coef_of(F.k2);
+        return nm;
+    }
+    static bool fast_same_shape(const Fast& A, const Fast& B) {
+        return A.need_f == B.need_f && A.anti == B.anti && is0(A.k1) == is0(B.k1) && is0(A.k2) == is0(B.k2) &&
+               ((A.k1.p ^ B.k1.p) & 1) == 0 && ((A.k2.p ^ B.k2.p) & 1) == 0;
+    }
+    // emits the pair update; logical registers k0 (x), k1 (y).  `track`: update names and deferred scales
+    void fast_pair(int k0, int k1, const Fast& F, const FastNames& nm, bool track) {
+        const int vx = phys[k0], vy = phys[k1];
+        if (F.need_f) P("  a%d = fma2(%s, sw(a%d), mul2(%s, a%d));", vy, nm.fi.c_str(), vy, nm.fr.c_str(), vy);
+        const int va = F.anti ? vy : vx, vb = F.anti ? vx : vy;       // A += k1 * B_old, B += k2 * A_old
+        const bool z1 = is0(F.k1), z2 = is0(F.k2);
+        if (!z1 && !z2)
+            P("  { const u64 t_ = a%d; a%d = fma2(%s, %s, a%d); a%d = fma2(%s, %s, a%d); }\n", va, va, nm.c1.c_str(), opnd_of(F.k1, V(vb)).c_str(), va,
+              vb, nm.c2.c_str(), opnd_of(F.k2, "t_").c_str(), vb);
+        else if (!z1) P("  a%d = fma2(%s, %s, a%d);\n", va, nm.c1.c_str(), opnd_of(F.k1, V(vb)).c_str(), va);
+        else if (!z2) P("  a%d = fma2(%s, %s, a%d);\n", vb, nm.c2.c_str(), opnd_of(F.k2, V(va)).c_str(), vb);
+        else if (F.need_f) P("\n");
+        if (!track) return;
+        if (F.anti) {
+            std::swap(phys[k0], phys[k1]);         // logical x now lives in what was y's variable
+            sc[vy] = F.ox;
+            sc[vx] = F.oy;
+        } else {
+            sc[vx] = F.ox;
+            sc[vy] = F.oy;
+        }
+    }
+
+    // -- self-contained form (three shears, explicit prescales): under run-time predicates
     struct ShearNames { std::string a, b, g, sx, sy, qy; };
     // force_sx / force_sy: emit the real prescale even when it is 1 (the other set of a per-thread select needs it)
     ShearNames names_for(const ShearSet& s, bool shi, bool force_sx = false, bool force_sy = false) {
@@ -182,9 +352,16 @@ struct Gen {
               x.c_str(), y.c_str(), nm.b.c_str(), x.c_str(), y.c_str(), x.c_str(), nm.g.c_str(), y.c_str(), x.c_str());
         }
     }
-    static void pair_regs(int tk, int p, int& k0, int& k1) {
-        k0 = ((p >> tk) << (tk + 1)) | (p & ((1 << tk) - 1));
-        k1 = k0 | (1 << tk);
+    std::vector<int> pair_vars(int tk, uint32_t pair_mask) const {
+        std::vector<int> v;
+        for (int p = 0; p < kPairs; ++p) {
+            if (!(pair_mask >> p & 1u)) continue;
+            int k0, k1;
+            pair_regs(tk, p, k0, k1);
+            v.push_back(phys[k0]);
+            v.push_back(phys[k1]);
+        }
+        return v;
     }
     void emit_shear(const TileOp& t) {
         const bool shi = t.kind == TK_SHI;
@@ -198,12 +375,75 @@ struct Gen {
         const std::string pe = pred_expr(t);
         const int tk = t.tk;
         P("  // %s tk=%d%s%s%s%s\n", shi ? "SHI" : "SHR", tk, mux ? " mux" : "", regmux ? " regmux" : "", py ? " py" : "", cy ? " cy" : "");
+        if (pe.empty()) {
+            // pair subsets known here: fast forms, deferred scales per register
+            for (int p = 0; p < kPairs; ++p) {
+                int k0, k1;
+                pair_regs(tk, p, k0, k1);
+                const ShearSet& s = (regmux && !((p >> t.mj) & 1)) ? B : A;
+                if (s.identity()) continue;
+                const Fast F = fast_form(s, shi, sc[phys[k0]], sc[phys[k1]]);
+                fast_pair(k0, k1, F, fast_names(F), true);
+            }
+            return;
+        }
+        // run-time predicate: the op's registers first get one common scale (it commutes with the op)
+        equalize(pair_vars(tk, 0xffffu));
         auto all_pairs = [&](const ShearSet& s, const ShearNames& nm) {
             for (int p = 0; p < kPairs; ++p) { int k0, k1; pair_regs(tk, p, k0, k1); shear_pair(k0, k1, s, nm, shi); }
         };
-        if (mux && !pe.empty()) {
+        if (mux) {
             // the multiplexing bit is a thread or tile-number bit: predicate true -> set a, false -> set b
             const bool lane_pred = (t.t_mask & 31u) != 0;
+            // fast forms when both branches leave the SAME deferred scales behind (a rotation and the same rotation
+            // times X: CX folded in); the two branches then differ only in coefficients and, maybe, in the pivot
+            if (!A.identity() && !B.identity()) {
+                const Sc one = Sc();
+                const Fast FA = fast_form(A, shi, one, one), FB = fast_form(B, shi, one, one);
+                if (sc_eq(FA.ox, FB.ox) && sc_eq(FA.oy, FB.oy)) {
+                    const Sc base = sc[phys[0]] ;     // (every register of the op has this scale now)
+                    (void)base;
+                    auto finish = [&](const Fast& F) {
+                        // both outputs of every pair: scale *= (ox, oy); names swap when the pivot is anti-diagonal
+                        for (int p = 0; p < kPairs; ++p) {
+                            int k0, k1;
+                            pair_regs(tk, p, k0, k1);
+                            const int vx = phys[k0], vy = phys[k1];
+                            const Sc s0 = sc[vx];
+                            if (F.anti) { std::swap(phys[k0], phys[k1]); sc[vy] = sc_mul(s0, F.ox); sc[vx] = sc_mul(s0, F.oy); }
+                            else { sc[vx] = sc_mul(s0, F.ox); sc[vy] = sc_mul(s0, F.oy); }
+                        }
+                    };
+                    if (fast_same_shape(FA, FB) && lane_pred) {
+                        const std::string ok = fresh("ok");
+                        P("  { const bool %s = %s;\n", ok.c_str(), pe.c_str());
+                        const FastNames na = fast_names(FA), nb = fast_names(FB);
+                        FastNames nm;
+                        auto sel = [&](const std::string& a, const std::string& b) {
+                            if (a.empty()) return std::string();
+                            const std::string v = fresh("k");
+                            P("  const u64 %s = %s ? %s : %s;\n", v.c_str(), ok.c_str(), a.c_str(), b.c_str());
+                            return v;
+                        };
+                        nm.fr = sel(na.fr, nb.fr); nm.fi = sel(na.fi, nb.fi); nm.c1 = sel(na.c1, nb.c1); nm.c2 = sel(na.c2, nb.c2);
+                        for (int p = 0; p < kPairs; ++p) { int k0, k1; pair_regs(tk, p, k0, k1); fast_pair(k0, k1, FA, nm, false); }
+                        P("  }\n");
+                        finish(FA);
+                        return;
+                    }
+                    if (FA.anti == FB.anti) {
+                        // same variables end up holding x and y in both branches: branch on the predicate
+                        const FastNames na = fast_names(FA), nb = fast_names(FB);
+                        P("  if (%s) {\n", pe.c_str());
+                        for (int p = 0; p < kPairs; ++p) { int k0, k1; pair_regs(tk, p, k0, k1); fast_pair(k0, k1, FA, na, false); }
+                        P("  } else {\n");
+                        for (int p = 0; p < kPairs; ++p) { int k0, k1; pair_regs(tk, p, k0, k1); fast_pair(k0, k1, FB, nb, false); }
+                        P("  }\n");
+                        finish(FA);
+                        return;
+                    }
+                }
+            }
             if (lane_pred && A.same_form(B) && !A.identity() && !B.identity()) {
                 // per-thread select of the coefficients, one instruction sequence (no divergence)
                 const std::string ok = fresh("ok");
@@ -230,7 +470,7 @@ struct Gen {
             }
             return;
         }
-        if (!pe.empty()) P("  if (%s) {\n", pe.c_str());
+        P("  if (%s) {\n", pe.c_str());
         if (regmux) {
             const ShearNames na = A.identity() ? ShearNames() : names_for(A, shi), nb = B.identity() ? ShearNames() : names_for(B, shi);
             for (int p = 0; p < kPairs; ++p) {
@@ -244,7 +484,7 @@ struct Gen {
         } else if (!A.identity()) {
             all_pairs(A, names_for(A, shi));
         }
-        if (!pe.empty()) P("  }\n");
+        P("  }\n");
     }
 
     // ---- direct kinds ---------------------------------------------------------------------------
@@ -256,30 +496,28 @@ struct Gen {
             const float c0 = t.a[0], c1 = t.a[1];
             P("  // PERM_%c tk=%d mask=%04x\n", imag ? 'I' : 'R', tk, t.mask & 0xffffu);
             if (pe.empty()) {
-                // x' = f0 * y, y' = f1 * x: scale in place, then swap the NAMES (exact data movement costs nothing)
-                const std::string f0 = imag ? IM(c0) : (c0 != 1.f ? BC(c0) : ""), f1 = imag ? IM(c1) : (c1 != 1.f ? BC(c1) : "");
+                // x' = f0 * y, y' = f1 * x: swap the NAMES, the factors go to the deferred scales (exact data movement costs nothing)
                 for (int p = 0; p < kPairs; ++p) {
                     if (!(t.mask >> p & 1u)) continue;
                     int k0, k1;
                     pair_regs(tk, p, k0, k1);
-                    const std::string x = R(k0), y = R(k1);
-                    if (imag) {
-                        P("  %s = mul2(%s, sw(%s)); %s = mul2(%s, sw(%s));\n", y.c_str(), f0.c_str(), y.c_str(), x.c_str(), f1.c_str(), x.c_str());
-                    } else {
-                        if (!f0.empty()) P("  %s = mul2(%s, %s);\n", y.c_str(), f0.c_str(), y.c_str());
-                        if (!f1.empty()) P("  %s = mul2(%s, %s);\n", x.c_str(), f1.c_str(), x.c_str());
-                    }
+                    const int vx = phys[k0], vy = phys[k1];
+                    sc[vy] = sc_mul(sc[vy], mk(c0, imag ? 1 : 0));
+                    sc[vx] = sc_mul(sc[vx], mk(c1, imag ? 1 : 0));
                     std::swap(phys[k0], phys[k1]);
                 }
             } else {
-                const std::string f0 = imag ? IM(c0) : BC(c0), f1 = imag ? IM(c1) : BC(c1);
+                equalize(pair_vars(tk, t.mask & 0xffffu));
+                const bool plain = !imag && c0 == 1.f && c1 == 1.f;
+                const std::string f0 = plain ? "" : (imag ? IM(c0) : BC(c0)), f1 = plain ? "" : (imag ? IM(c1) : BC(c1));
                 P("  if (%s) {\n", pe.c_str());
                 for (int p = 0; p < kPairs; ++p) {
                     if (!(t.mask >> p & 1u)) continue;
                     int k0, k1;
                     pair_regs(tk, p, k0, k1);
                     const std::string x = R(k0), y = R(k1);
-                    if (imag) P("  { const u64 t_ = %s; %s = mul2(%s, sw(%s)); %s = mul2(%s, sw(t_)); }\n", x.c_str(), x.c_str(), f0.c_str(), y.c_str(), y.c_str(), f1.c_str());
+                    if (plain) P("  { const u64 t_ = %s; %s = %s; %s = t_; }\n", x.c_str(), x.c_str(), y.c_str(), y.c_str());
+                    else if (imag) P("  { const u64 t_ = %s; %s = mul2(%s, sw(%s)); %s = mul2(%s, sw(t_)); }\n", x.c_str(), x.c_str(), f0.c_str(), y.c_str(), y.c_str(), f1.c_str());
                     else P("  { const u64 t_ = %s; %s = mul2(%s, %s); %s = mul2(%s, t_); }\n", x.c_str(), x.c_str(), f0.c_str(), y.c_str(), y.c_str(), f1.c_str());
                 }
                 P("  }\n");
@@ -288,6 +526,7 @@ struct Gen {
         }
         // TK_GEN: x' = m00 x + m01 y, y' = m10 x + m11 y
         P("  // GEN tk=%d mask=%04x\n", tk, t.mask & 0xffffu);
+        equalize(pair_vars(tk, t.mask & 0xffffu));
         if (!pe.empty()) P("  if (%s) {\n", pe.c_str());
         std::string re[4], im[4];
         for (int i = 0; i < 4; ++i) { re[i] = BC(t.a[2 * i]); im[i] = IM(t.a[2 * i + 1]); }
@@ -307,15 +546,25 @@ struct Gen {
     void emit_factor(const TileOp& t) {
         const std::string pe = pred_expr(t);
         P("  // FACTOR kind=%d mask=%08x\n", (int)t.kind, t.mask);
-        if (!pe.empty()) P("  if (%s) {\n", pe.c_str());
         if (t.kind == TK_SCALE_R || t.kind == TK_SCALE_I) {
+            if (pe.empty()) {
+                // a real or imaginary factor on whole registers: deferred, no instruction
+                for (int k = 0; k < kRegs; ++k)
+                    if (t.mask >> k & 1u) sc[phys[k]] = sc_mul(sc[phys[k]], mk(t.a[0], t.kind == TK_SCALE_I ? 1 : 0));
+                return;
+            }
+            P("  if (%s) {\n", pe.c_str());
             const std::string f = t.kind == TK_SCALE_R ? BC(t.a[0]) : IM(t.a[0]);
             for (int k = 0; k < kRegs; ++k) {
                 if (!(t.mask >> k & 1u)) continue;
                 if (t.kind == TK_SCALE_R) P("  %s = mul2(%s, %s);\n", R(k).c_str(), f.c_str(), R(k).c_str());
                 else P("  %s = mul2(%s, sw(%s));\n", R(k).c_str(), f.c_str(), R(k).c_str());
             }
-        } else {
+            P("  }\n");
+            return;
+        }
+        if (!pe.empty()) P("  if (%s) {\n", pe.c_str());
+        {
             // e^{i theta} as three shears on (re, im); TK_PHASE_N starts from the negated amplitude
             const std::string c = C(pack2(t.a[0], t.a[1]));
             P("  { const float fr = lo(%s), fi = hi(%s);\n", c.c_str(), c.c_str());
@@ -404,6 +653,7 @@ struct Gen {
                 if (k >> i & 1) c ^= rcol[i];
             return c;
         };
+        materialize_all();
         P("  SYNC();\n  {\n");
         emit_cols("wb", sg.wr_tcol);
         bool low_w[16] = {false}, low_r[16] = {false};
@@ -505,18 +755,24 @@ struct Gen {
                 }
             }
         }
+        materialize_all();
         P("  {\n");
         io_base("dst", fp.st_toff);
         std::string re, im;
-        if (fp.has_scale) {
-            re = BC(fp.scale.x);
-            if (fp.scale.y != 0.f) im = IM(fp.scale.y);
+        {
+            const std::complex<double> fin = gscale * (fp.has_scale ? std::complex<double>(fp.scale.x, fp.scale.y) : std::complex<double>(1.0, 0.0));
+            const bool real_only = std::fabs(fin.imag()) <= 1e-9 * std::abs(fin), imag_only = std::fabs(fin.real()) <= 1e-9 * std::abs(fin);
+            if (!(real_only && std::fabs(fin.real() - 1.0) <= 1e-9)) {
+                if (!imag_only) re = BC((float)fin.real());
+                if (!real_only) im = IM((float)fin.imag());
+            }
         }
         for (int k = 0; k < kRegs; ++k) {
             const std::string r = R(k);
             const unsigned long long off = (unsigned long long)reg_off(fp.st_roff, k);
-            if (!fp.has_scale) P("  STG(dst + 0x%llxull, %s);\n", off, r.c_str());
+            if (re.empty() && im.empty()) P("  STG(dst + 0x%llxull, %s);\n", off, r.c_str());
             else if (im.empty()) P("  STG(dst + 0x%llxull, mul2(%s, %s));\n", off, re.c_str(), r.c_str());
+            else if (re.empty()) P("  STG(dst + 0x%llxull, mul2(%s, sw(%s)));\n", off, im.c_str(), r.c_str());
             else P("  STG(dst + 0x%llxull, fma2(%s, sw(%s), mul2(%s, %s)));\n", off, im.c_str(), r.c_str(), re.c_str(), r.c_str());
         }
         P("  }\n");
@@ -546,7 +802,9 @@ bool spec_generate(int n, const FusedPass& fp, SpecSource& out, std::string& why
                  NT, nc, 1u << fp.T);
         head += buf;
         for (size_t i = 0; i < nc; ++i) { snprintf(buf, sizeof buf, "  const u64 c%zu = cc[%zu];\n", i, i); head += buf; }
-        snprintf(buf, sizeof buf, "#else\n#define SYNC() __syncthreads()\nextern \"C\" __global__ void __launch_bounds__(AQS_NT, %d) aqs_pass(const RT rt", tile_min_blocks(fp.T));
+        int minb = tile_min_blocks(fp.T);
+        if (const char* e = std::getenv("AQS_JIT_MINB")) minb = std::max(1, std::atoi(e));      // (experiments)
+        snprintf(buf, sizeof buf, "#else\n#define SYNC() __syncthreads()\nextern \"C\" __global__ void __launch_bounds__(AQS_NT, %d) aqs_pass(const RT rt", minb);
         head += buf;
         for (size_t i = 0; i < nc; ++i) { snprintf(buf, sizeof buf, ", const u64 c%zu", i); head += buf; }
         head += ") {\n  extern __shared__ __align__(16) u64 sm[];\n  const u32 TID = threadIdx.x, BID = blockIdx.x;\n#endif\n";
@@ -591,16 +849,34 @@ struct Nvrtc {
     int (*GetProgramLog)(nvrtcProgram_t, char*) = nullptr;
     int (*DestroyProgram)(nvrtcProgram_t*) = nullptr;
     bool ok = false;
+    int version = 0;       // major * 1000 + minor
     std::string err;
 };
 Nvrtc g_nvrtc;
 std::once_flag g_nvrtc_once;
 
 void load_nvrtc() {
-    static const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    // Several NVRTC builds can be visible to one process (a Python environment bundles its own next to the toolkit's,
+    // and dlopen by SONAME returns whichever was loaded first).  Code quality differs between them — measured on the
+    // brickwork-30 plan: 63.7 ms with NVRTC 12.9, 75.8 ms with the 12.8 build that PyTorch ships — so every candidate is
+    // opened and the NEWEST one is used.  AQS_NVRTC_LIB forces a specific file.
+    static const char* names[] = {"/usr/local/cuda/lib64/libnvrtc.so.13", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                                  "libnvrtc.so.13", "libnvrtc.so.12", "libnvrtc.so"};
     void* h = nullptr;
-    if (const char* e = std::getenv("AQS_NVRTC_LIB")) h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
-    for (size_t i = 0; !h && i < sizeof names / sizeof *names; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+    if (const char* e = std::getenv("AQS_NVRTC_LIB")) {
+        h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+    } else {
+        int best = -1;
+        for (size_t i = 0; i < sizeof names / sizeof *names; ++i) {
+            void* c = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+            if (!c) continue;
+            int major = 0, minor = 0;
+            auto ver = reinterpret_cast<int (*)(int*, int*)>(dlsym(c, "nvrtcVersion"));
+            const int v = (ver && ver(&major, &minor) == 0) ? major * 1000 + minor : 0;
+            if (v > best) { best = v; h = c; }
+        }
+        g_nvrtc.version = best;
+    }
     if (!h) { g_nvrtc.err = "libnvrtc.so.12 not found"; return; }
 #define AQS_SYM(field, sym) g_nvrtc.field = reinterpret_cast<decltype(g_nvrtc.field)>(dlsym(h, sym)); if (!g_nvrtc.field) { g_nvrtc.err = "missing " sym; return; }
     AQS_SYM(CreateProgram, "nvrtcCreateProgram")
@@ -760,11 +1036,31 @@ Pool& pool() {
 
 int spec_attach(int n, std::vector<FusedPass>& passes, bool wait) {
     Pool& pl = pool();
+    // 1. generate every pass's source; long circuits repeat their pass shapes (Grover-26, 64 iterations: 259 passes, 9 shapes)
+    std::vector<SpecSource> srcs(passes.size());
+    std::vector<char> have(passes.size(), 0);
+    size_t n_new = 0;
+    {
+        std::vector<uint64_t> fresh_keys;
+        for (size_t i = 0; i < passes.size(); ++i) {
+            std::string why;
+            if (!spec_generate(n, passes[i], srcs[i], why)) continue;       // this pass stays on the generic kernel
+            have[i] = 1;
+            std::lock_guard<std::mutex> lk(pl.mu);
+            if (pl.cache.find(srcs[i].key) == pl.cache.end() && std::find(fresh_keys.begin(), fresh_keys.end(), srcs[i].key) == fresh_keys.end())
+                fresh_keys.push_back(srcs[i].key);
+        }
+        n_new = fresh_keys.size();
+    }
+    size_t max_new = 128;              // a plan that needs more NEW kernels than this is not worth their compilation
+    if (const char* e = std::getenv("AQS_JIT_MAX_KERNELS")) max_new = (size_t)std::max(0, std::atoi(e));
+    if (n_new > max_new) return AQS_OK;
+    // 2. look the shapes up / queue their compilation
     std::vector<std::shared_ptr<SpecKernel>> mine;
-    for (FusedPass& fp : passes) {
-        SpecSource s;
-        std::string why;
-        if (!spec_generate(n, fp, s, why)) continue;       // this pass stays on the interpreter
+    for (size_t i = 0; i < passes.size(); ++i) {
+        if (!have[i]) continue;
+        FusedPass& fp = passes[i];
+        SpecSource& s = srcs[i];
         std::shared_ptr<SpecKernel> k;
         {
             std::lock_guard<std::mutex> lk(pl.mu);
@@ -786,7 +1082,7 @@ int spec_attach(int n, std::vector<FusedPass>& passes, bool wait) {
             }
         }
         pl.cv_work.notify_one();
-        if (k->n_coefs != s.coefs.size()) continue;        // hash collision: keep the interpreter
+        if (k->n_coefs != s.coefs.size()) continue;        // hash collision: keep the generic kernel
         fp.spec = k;
         fp.spec_coefs = std::move(s.coefs);
         mine.push_back(k);

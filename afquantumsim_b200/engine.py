@@ -64,6 +64,7 @@ ABI_SYMBOLS = [
     "aqs_state_ipc_export", "aqs_ipc_open", "aqs_ipc_close_all", "aqs_peer_bitswap",
     "aqs_apply_dense", "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span", "aqs_plan_shard_cut",
     "aqs_plan_pass_source", "aqs_plan_pass_coefs", "aqs_plan_jit_ready", "aqs_jit_wait", "aqs_jit_get_info",
+    "aqs_sample_hist_sparse", "aqs_pool_trim",
 ]
 
 
@@ -106,6 +107,7 @@ def load():
         "aqs_plan_shard_cut": [vp, u64, i32, i32, P(ctypes.c_uint32), P(ctypes.c_uint32), P(ctypes.c_uint8)],
         "aqs_plan_pass_source": [vp, u64, vp, u64, P(u64), P(u64)], "aqs_plan_pass_coefs": [vp, u64, vp, u64, P(u64)],
         "aqs_plan_jit_ready": [vp, P(u64)], "aqs_jit_wait": [], "aqs_jit_get_info": [P(JitInfo)],
+        "aqs_sample_hist_sparse": [vp, vp, u64, vp, vp, u64, P(u64)], "aqs_pool_trim": [],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -481,3 +483,17 @@ class State:
         _check(load().aqs_sample_hist(self._h, u.ctypes.data_as(ctypes.c_void_p), u.size,
                                       hist.ctypes.data_as(ctypes.c_void_p)))
         return hist
+
+    def sample_hist_sparse(self, u: np.ndarray):
+        """profile_measure_all as sorted (index, count) pairs: 8 bytes per draw cross the bus, no dense 2^n vector."""
+        u = np.ascontiguousarray(u, dtype=np.float32)
+        idx = np.empty(max(1, u.size), dtype=np.uint64)
+        cnt = np.empty(max(1, u.size), dtype=np.uint32)
+        bins = ctypes.c_uint64()
+        _check(load().aqs_sample_hist_sparse(self._h, u.ctypes.data_as(ctypes.c_void_p), u.size, idx.ctypes.data_as(ctypes.c_void_p),
+                                             cnt.ctypes.data_as(ctypes.c_void_p), idx.size, ctypes.byref(bins)))
+        return idx[:bins.value].copy(), cnt[:bins.value].copy()
+
+
+def pool_trim() -> None:
+    _check(load().aqs_pool_trim())

@@ -53,6 +53,10 @@ void clear_circuit_cache();
 void set_seed(uint64_t seed);
 /* Gate fusion for simulate()/compile() plans (default on; $AQS_FUSION=0 turns it off). */
 void set_fusion(bool on);
+/* specialised (run-time compiled) pass kernels are requested for circuits on at least this many qubits (default 26;
+ * AQS_JIT_MIN_QUBITS): compile() waits for them, an uncompiled simulate() lets them compile in the background */
+void set_jit_min_qubits(int n);
+void jit_wait();   /* block until no kernel compilation is pending */
 bool get_fusion();
 
 /* Collects the primitive ops a gate lowers to. */
@@ -192,7 +196,8 @@ class QCircuit {
     uint32_t qubits_          = 0;
     std::size_t cached_index_ = 0;
     std::shared_ptr<std::vector<aqs_op>> compiled_ops_;
-    mutable std::shared_ptr<detail::PlanCache> plan_;
+    mutable std::shared_ptr<detail::PlanCache> plan_;        /* compiled prefix */
+    mutable std::shared_ptr<detail::PlanCache> tail_plan_;   /* last uncompiled tail that was simulated (reused while its ops do not change) */
     mutable std::shared_ptr<af::array> matrix_;
     void detach();
 };

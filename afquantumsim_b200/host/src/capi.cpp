@@ -59,6 +59,8 @@ int aqsh_initialize(int device) {
 }
 void aqsh_set_seed(uint64_t seed) { set_seed(seed); }
 void aqsh_set_fusion(int on) { set_fusion(on != 0); }
+void aqsh_set_jit_min_qubits(int n) { set_jit_min_qubits(n); }
+void aqsh_jit_wait() { jit_wait(); }
 int aqsh_get_fusion() { return get_fusion() ? 1 : 0; }
 void aqsh_clear_circuit_cache() { clear_circuit_cache(); }
 

@@ -88,6 +88,14 @@ class ShardedPlan:
         self.steps, self.entry_pos, self.exit_pos = steps, list(entry_pos), list(exit_pos)
         self.n_exchanges = self.exchange_bytes = self.n_local_ops = self.n_passes = 0
 
+    def jit_ready(self) -> int:
+        """fused passes that would run on their specialised kernel now (flat plans)"""
+        return sum(step[1].jit_ready() for step in self.steps if step[0] in ("flat", "plan"))
+
+    def spans(self) -> list:
+        """rank bits inside the tile of every pass of a flat plan (0 = the pass stays inside the shards)"""
+        return [j for step in self.steps if step[0] == "flat" for j in step[2]]
+
 
 class _CudaMem:
     """__cuda_array_interface__ view of engine-owned device memory (lets torch / NCCL address a shard)."""
@@ -100,8 +108,9 @@ class _Sched:
     """Layout bookkeeping while a schedule is emitted: local op records pile up in `pending` until a remap
     (or the end) turns them into one fused plan."""
 
-    def __init__(self, st: "ShardedState"):
+    def __init__(self, st: "ShardedState", wait: bool = True):
         self.st = st
+        self.wait = wait        # do fused local plans wait for their specialised kernels?
         self.pos = list(st.pos)
         self.steps: list = []
         self.pending: List[np.ndarray] = []
@@ -114,7 +123,8 @@ class _Sched:
         if self.pending:
             st = self.st
             ops = np.concatenate(self.pending)
-            self.steps.append(("plan", eng.Plan(st.n_local, ops, eng.PLAN_FUSE if st.fuse else 0), len(ops)))
+            flags = (eng.PLAN_FUSE | st._jit_flags(self.wait)) if st.fuse else 0
+            self.steps.append(("plan", eng.Plan(st.n_local, ops, flags), len(ops)))
             self.pending = []
 
     def local_swap(self, pa: int, pb: int):
@@ -168,8 +178,9 @@ class ShardedState:
     """A 2^n complex64 state vector sharded over the ranks of a torch.distributed group."""
 
     def __init__(self, n_qubits: int, device: Optional[torch.device] = None, group=None, fuse: bool = True,
-                 p2p: Optional[bool] = None, flat: Optional[bool] = None):
+                 p2p: Optional[bool] = None, flat: Optional[bool] = None, jit: Optional[bool] = None):
         self.group = group
+        self.jit = jit          # specialised pass kernels: None = automatic (shards of 2^26 amplitudes and more)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.g = int(math.log2(self.world))
@@ -213,7 +224,7 @@ class ShardedState:
         Needs shards that are a multiple of the 2 MiB mapping granularity; all-or-nothing across ranks."""
         shard_bytes = 8 << self.n_local
         ok, space, fds = 1, None, {}
-        if shard_bytes % (2 << 20) or self.n_local < 12 + self.g:
+        if shard_bytes % (2 << 20) or self.n_local < 13 + self.g:
             return False            # the same answer on every rank: no consensus round needed
 
         def agreed(value: int) -> bool:
@@ -429,7 +440,14 @@ class ShardedState:
         return 1 << 30
 
     # ------------------------------------------------------------------ gates
-    def compile(self, records: np.ndarray) -> ShardedPlan:
+    def _jit_flags(self, wait: bool) -> int:
+        """specialised pass kernels: on by request, else for shards of 2^26 amplitudes and more (like the host layer)"""
+        on = self.jit if self.jit is not None else self.n_local >= 26
+        if not on or self.device.type != "cuda":
+            return 0
+        return eng.PLAN_JIT if wait else eng.PLAN_JIT_ASYNC
+
+    def compile(self, records: np.ndarray, wait: bool = True) -> ShardedPlan:
         """Schedule primitive ops (struct aqs_op records over all n qubits, API numbering) for the CURRENT
         layout: everything executable between two remaps becomes one fused local plan.  On a flat
         address space there is nothing to schedule: ONE fused plan over all n qubits, no remaps."""
@@ -437,7 +455,7 @@ class ShardedState:
             recs = np.ascontiguousarray(records, dtype=eng.OP_DTYPE)
             plan = ShardedPlan([], self.pos, self.pos)
             if len(recs):
-                ep = eng.Plan(self.n, recs, eng.PLAN_FUSE)
+                ep = eng.Plan(self.n, recs, eng.PLAN_FUSE | self._jit_flags(wait))
                 n_passes = int(ep.info()["n_fused_passes"])
                 spans = [ep.pass_span(i, self.g) for i in range(n_passes)]
                 plan.steps.append(("flat", ep, spans, len(recs)))
@@ -447,7 +465,7 @@ class ShardedState:
                 plan.n_exchanges = sum(1 for j in spans if j)
                 plan.exchange_bytes = sum((8 << self.n_local) * ((1 << j) - 1) // (1 << j) for j in spans)
             return plan
-        sch = _Sched(self)
+        sch = _Sched(self, wait)
         pos = sch.pos
         remaining = [_Op(r) for r in np.ascontiguousarray(records, dtype=eng.OP_DTYPE)]
         while remaining:
@@ -537,8 +555,8 @@ class ShardedState:
             self._stream_barrier()
 
     def apply_ops(self, records: np.ndarray):
-        """Apply primitive ops: compile for the current layout, then run."""
-        self.run(self.compile(records))
+        """Apply primitive ops: compile for the current layout (kernels of new pass shapes compile in the background), then run."""
+        self.run(self.compile(records, wait=False))
 
     def run_circuit(self, qc) -> None:
         """simulate() for an afquantumsim_b200.aqs.QCircuit on more qubits than one GPU holds."""

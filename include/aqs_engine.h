@@ -210,9 +210,16 @@ int aqs_sample(aqs_state_t s, const float* u_host, uint64_t n_draws, uint64_t* o
  * minus the probability mass of lower-ranked shards): the sharded sampler's local step.
  * out = local index of the first S_k > U, or UINT64_MAX if U >= the shard's total. */
 int aqs_sample_fixed(aqs_state_t s, const uint64_t* u_fixed_host, uint64_t n_draws, uint64_t* out_index_host);
-/* same, reduced on the device to the dense histogram profile_measure_all returns
- * (std::vector<uint32_t>(2^n), src/quantum.cpp:470,498); hist_host has 2^n entries */
+/* same, as the dense histogram profile_measure_all returns (std::vector<uint32_t>(2^n),
+ * src/quantum.cpp:470,498); hist_host has 2^n entries.  Only the n_draws outcome indices cross the bus
+ * (8 bytes per draw); the dense vector is filled on the host. */
 int aqs_sample_hist(aqs_state_t s, const float* u_host, uint64_t n_draws, uint32_t* hist_host);
+/* the same histogram as sorted (index, count) pairs: what the reference's sort + countByKey produce
+ * before they are scattered into the dense vector (src/quantum.cpp:490-498).  *n_bins gets the number of
+ * distinct outcomes (<= n_draws); the pairs are written when index / count are non-null and cap >= *n_bins.
+ * This is the histogram API for states above 30 qubits, where a dense vector is not an option. */
+int aqs_sample_hist_sparse(aqs_state_t s, const float* u_host, uint64_t n_draws, uint64_t* index_host, uint32_t* count_host,
+                           uint64_t cap, uint64_t* n_bins);
 
 /* ---- peer memory: sharded states on one NVLink / NVSwitch node -------------------
  * No reference counterpart (the reference is single-device).  A state of
@@ -270,6 +277,9 @@ typedef struct aqs_counters {
 } aqs_counters;
 int aqs_counters_get(aqs_counters* out);
 int aqs_counters_reset(void);
+/* give every cached device buffer back to the driver (the engine recycles state-sized buffers between states;
+ * other allocators of the process — torch, NCCL, the flat address space — do not see that cache) */
+int aqs_pool_trim(void);
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,34 @@ int aqs_sample_hist(aqs_state_t s, const float* u, uint64_t n, uint32_t* hist) {
     free(idx); return AQS_OK;
 }
 
+static int cmp_u64(const void* a, const void* b) { uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : x > y; }
+int aqs_sample_hist_sparse(aqs_state_t s, const float* u, uint64_t n, uint64_t* index, uint32_t* count, uint64_t cap, uint64_t* n_bins) {
+    REQ(s && n_bins && (u || n == 0), "null"); *n_bins = 0; if (n == 0) return AQS_OK;
+    uint64_t* idx = (uint64_t*)malloc(sizeof(uint64_t) * n);
+    if (orc_sample(s->a, s->n, u, n, idx, 0)) { free(idx); return fail(AQS_ERR_NOMEM, "sample"); }
+    qsort(idx, n, sizeof(uint64_t), cmp_u64);
+    uint64_t bins = 0;
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i; while (j < n && idx[j] == idx[i]) ++j;
+        if (index && count && bins < cap) { index[bins] = idx[i]; count[bins] = (uint32_t)(j - i); }
+        ++bins; i = j;
+    }
+    free(idx); *n_bins = bins;
+    if (index && count && bins > cap) return fail(AQS_ERR_INVALID, "histogram has more bins than the output arrays hold");
+    return AQS_OK;
+}
+int aqs_pool_trim(void) { return AQS_OK; }
+int aqs_jit_wait(void) { return AQS_OK; }
+/* specialised pass kernels exist only in the CUDA engine: the stand-in has no fused passes to specialise */
+int aqs_plan_pass_source(aqs_plan_t p, uint64_t index, char* buf, uint64_t cap, uint64_t* needed, uint64_t* geom) {
+    (void)p; (void)index; (void)buf; (void)cap; (void)needed; (void)geom; return fail(AQS_ERR_STATE, "no fused passes in the CPU stand-in");
+}
+int aqs_plan_pass_coefs(aqs_plan_t p, uint64_t index, uint64_t* buf, uint64_t cap, uint64_t* needed) {
+    (void)p; (void)index; (void)buf; (void)cap; (void)needed; return fail(AQS_ERR_STATE, "no fused passes in the CPU stand-in");
+}
+int aqs_plan_jit_ready(aqs_plan_t p, uint64_t* n_ready) { REQ(p && n_ready, "null"); *n_ready = 0; return AQS_OK; }
+int aqs_jit_get_info(aqs_jit_info* out) { REQ(out, "null"); memset(out, 0, sizeof *out); return AQS_OK; }
+
 /* opaque k-qubit matrix on arbitrary qubits: plain loops (the oracle's orc_apply_dense restates the
  * reference's contiguous Gate / ControlGate embedding; tests compare the two) */
 int aqs_apply_dense(aqs_state_t s, const int* qubits, int k, uint64_t ctrl_mask, uint64_t ctrl_value, const aqs_c32* m) {

@@ -322,7 +322,7 @@ def test_fused_permutation_circuits_are_exact(seed):
     assert np.array_equal(gpu_run(n, init, circ, fuse=True), orc.simulate(init.copy(), circ))
 
 
-@pytest.mark.parametrize("tile_bits", [10, 11, 13])
+@pytest.mark.parametrize("tile_bits", [10, 11, 12])
 def test_other_tile_sizes(tile_bits, monkeypatch):
     """the tile kernel is instantiated for 10..13 tile bits; AQS_TILE_BITS selects one at plan time"""
     monkeypatch.setenv("AQS_TILE_BITS", str(tile_bits))

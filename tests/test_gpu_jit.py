@@ -76,7 +76,7 @@ def test_qft_closed_form_and_grover():
     assert orc.rel_l2(run(n, init, lower_array(circ), JIT), orc.simulate(init.copy(), circ)) < TOL
 
 
-@pytest.mark.parametrize("tile_bits", [10, 11, 13])
+@pytest.mark.parametrize("tile_bits", [10, 11, 12])
 def test_other_tile_sizes(tile_bits, monkeypatch):
     monkeypatch.setenv("AQS_TILE_BITS", str(tile_bits))
     n = 16

@@ -22,7 +22,7 @@ def test_unfused_plan_counts_every_gate():
 
 def test_brickwork30_fuses_into_few_passes():
     i = info(30, wl.to_ops(wl.brickwork(30, 20)))
-    assert i["n_single_ops"] == 0 and i["tile_bits"] == 12
+    assert i["n_single_ops"] == 0 and i["tile_bits"] == 13
     assert i["n_fused_passes"] <= 40
     assert i["bytes_planned"] == i["n_fused_passes"] * 2 * 8.0 * 2 ** 30
     assert i["bytes_planned"] < i["bytes_unfused"] / 15

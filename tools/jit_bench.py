@@ -13,11 +13,18 @@ from afquantumsim_b200 import workloads as wl  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 eng.init(0)
-ops = wl.to_ops(wl.brickwork(n, 20))
+import os
+if os.environ.get("BENCH_OPS") == "aqs":
+    from afquantumsim_b200 import aqs
+    aqs.initialize(0)
+    ops = aqs.QCircuit(n).extend(wl.brickwork(n, 20)).ops()
+else:
+    ops = wl.to_ops(wl.brickwork(n, 20))
 st = eng.State(n)
 timer = eng.Timer()
 out = {"n": n}
-for name, flags in (("interp", eng.PLAN_FUSE), ("jit", eng.PLAN_FUSE | eng.PLAN_JIT)):
+legs = (("jit", eng.PLAN_FUSE | eng.PLAN_JIT),) if os.environ.get("BENCH_JIT_ONLY") else (("interp", eng.PLAN_FUSE), ("jit", eng.PLAN_FUSE | eng.PLAN_JIT))
+for name, flags in legs:
     t0 = time.perf_counter()
     plan = eng.Plan(n, ops, flags)
     build_s = time.perf_counter() - t0
