@@ -23,6 +23,12 @@
 
 #include "engine_internal.h"
 
+struct aqs_flat_view_s {
+    CUdeviceptr base = 0;
+    size_t bytes = 0;
+    std::vector<std::pair<CUdeviceptr, size_t>> maps;    // mapped sub-ranges
+};
+
 struct aqs_flat_s {
     int world = 0, rank = 0, device = 0;
     size_t shard_bytes = 0;
@@ -30,6 +36,13 @@ struct aqs_flat_s {
     std::vector<CUmemGenericAllocationHandle> handles;
     std::vector<char> mapped;
     int own_fd = -1;
+    // staged passes: local staging memory for the peers' parts of a pass's tiles, and views of the state in which
+    // those parts ARE the staging memory
+    // (cuMemMap cannot map a PART of an allocation — its offset must be zero — so the staging memory is a pool of
+    // block-sized allocations, shared by all views: only one staged pass runs at a time)
+    std::vector<std::pair<size_t, CUmemGenericAllocationHandle>> stage_blocks;    // (bytes, handle)
+    size_t granularity = 0;
+    std::vector<aqs_flat_view_s*> views;
 };
 
 namespace {
@@ -134,6 +147,7 @@ int aqs_flat_create(uint64_t shard_bytes, int world, int rank, aqs_flat_t* out, 
     aqs_flat_s* f = new (std::nothrow) aqs_flat_s();
     if (!f) return aqs::fail(AQS_ERR_NOMEM, "host allocation failed");
     f->world = world; f->rank = rank; f->device = device; f->shard_bytes = (size_t)shard_bytes;
+    f->granularity = gran;
     f->handles.assign(world, 0);
     f->mapped.assign(world, 0);
     CUmemGenericAllocationHandle h = 0;
@@ -175,9 +189,93 @@ int aqs_flat_ptr(aqs_flat_t f, void** base, void** own_shard) {
     return AQS_OK;
 }
 
+// ---- staged passes ---------------------------------------------------------------------------------------------
+// A pass whose tiles contain rank bits needs, on every GPU, parts of the peers' shards.  Reading them from inside the
+// kernel means scattered 256-byte reads over NVLink, which run at about half the link rate (measured on 2 x B200: 425 GB/s
+// against 790 GB/s for contiguous reads; peer WRITES reach 718 GB/s whatever the pattern: profiles/r02_peer_bw.txt).  The
+// parts a rank needs are large contiguous blocks though (the tiles of a rank are selected by pinning high local bits), so
+// the copy engines fetch them into local STAGING memory in big pieces while the kernel computes the previous chunk of
+// tiles, and the kernel reads a VIEW of the state — a second virtual range in which this rank's shard is mapped as usual
+// and the needed blocks of the peers' slots are backed by local staging allocations (the copies write through the view's
+// own addresses) — while it still writes its results directly into the peers' HBM.
+static void view_free(aqs_flat_view_s* v) {
+    for (auto& m : v->maps) g_drv.MemUnmap(m.first, m.second);
+    if (v->base) g_drv.MemAddressFree(v->base, v->bytes);
+    delete v;
+}
+
+int aqs_flat_view_create(aqs_flat_t f, const aqs_flat_block* blocks, uint64_t n_blocks, void** view_base) {
+    if (!f || !view_base || (!blocks && n_blocks)) return aqs::fail(AQS_ERR_INVALID, "null argument");
+    const size_t total = f->shard_bytes * (size_t)f->world;
+    for (uint64_t i = 0; i < n_blocks; ++i) {
+        const aqs_flat_block& b = blocks[i];
+        if (b.bytes == 0 || b.bytes % f->granularity || b.state_offset % f->granularity || b.state_offset + b.bytes > total)
+            return aqs::fail(AQS_ERR_INVALID, "staged block is misaligned or out of range");
+        const size_t s0 = b.state_offset / f->shard_bytes, s1 = (b.state_offset + b.bytes - 1) / f->shard_bytes;
+        if (s0 != s1 || (int)s0 == f->rank) return aqs::fail(AQS_ERR_INVALID, "a staged block must lie inside ONE peer shard");
+    }
+    aqs_flat_view_s* v = new (std::nothrow) aqs_flat_view_s();
+    if (!v) return aqs::fail(AQS_ERR_NOMEM, "host allocation failed");
+    v->bytes = total;
+    CUresult r = g_drv.MemAddressReserve(&v->base, total, 1ull << 21, 0, 0);
+    if (r != CUDA_SUCCESS) { delete v; return fail_drv(r, "cuMemAddressReserve(view)"); }
+    CUmemAccessDesc acc;
+    std::memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = f->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    auto map = [&](CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle h) {
+        CUresult q = g_drv.MemMap(va, bytes, 0, h, 0);
+        if (q != CUDA_SUCCESS) return q;
+        v->maps.push_back({va, bytes});
+        return g_drv.MemSetAccess(va, bytes, &acc, 1);
+    };
+    r = map(v->base + (CUdeviceptr)f->rank * f->shard_bytes, f->shard_bytes, f->handles[f->rank]);
+    // staging blocks from the pool: the k-th block of a given size of this view takes the k-th pooled allocation of that size
+    CUmemAllocationProp prop;
+    std::memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = f->device;
+    std::vector<char> used(f->stage_blocks.size(), 0);
+    for (uint64_t i = 0; r == CUDA_SUCCESS && i < n_blocks; ++i) {
+        size_t k = 0;
+        while (k < f->stage_blocks.size() && (used[k] || f->stage_blocks[k].first != blocks[i].bytes)) ++k;
+        if (k == f->stage_blocks.size()) {
+            CUmemGenericAllocationHandle h = 0;
+            r = g_drv.MemCreate(&h, blocks[i].bytes, &prop, 0);
+            if (r == CUDA_ERROR_OUT_OF_MEMORY) {
+                aqs_pool_trim();
+                r = g_drv.MemCreate(&h, blocks[i].bytes, &prop, 0);
+            }
+            if (r != CUDA_SUCCESS) break;
+            f->stage_blocks.push_back({(size_t)blocks[i].bytes, h});
+            used.push_back(0);
+        }
+        used[k] = 1;
+        r = map(v->base + blocks[i].state_offset, blocks[i].bytes, f->stage_blocks[k].second);
+    }
+    if (r != CUDA_SUCCESS) { view_free(v); return r == CUDA_ERROR_OUT_OF_MEMORY ? aqs::fail(AQS_ERR_NOMEM, "staging memory: out of device memory") : fail_drv(r, "mapping a view of the state"); }
+    f->views.push_back(v);
+    *view_base = (void*)v->base;
+    return AQS_OK;
+}
+
+// plain asynchronous device-to-device copy on a stream (local or peer addresses of the flat range, the staging buffer)
+int aqs_memcpy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+    if (!dst || !src) return aqs::fail(AQS_ERR_INVALID, "null argument");
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return aqs::fail_cuda(e, "cudaMemcpyAsync(device to device)", __LINE__);
+    return AQS_OK;
+}
+
 int aqs_flat_destroy(aqs_flat_t f) {
     if (!f) return AQS_OK;
     cudaDeviceSynchronize();
+    for (aqs_flat_view_s* v : f->views) view_free(v);
+    f->views.clear();
+    for (auto& sb : f->stage_blocks) g_drv.MemRelease(sb.second);
+    f->stage_blocks.clear();
     for (int s = 0; s < f->world; ++s) {
         if (f->mapped[s]) g_drv.MemUnmap(f->base + (CUdeviceptr)s * f->shard_bytes, f->shard_bytes);
         if (f->handles[s]) g_drv.MemRelease(f->handles[s]);

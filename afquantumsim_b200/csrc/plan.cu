@@ -1199,9 +1199,10 @@ static int ensure_uploaded(aqs_plan_s* p) {
     return AQS_OK;
 }
 
-static void fill_params(PassParams& P, float2* state, const FusedPass& fp) {
+static void fill_params(PassParams& P, float2* state, float2* state_out, const FusedPass& fp) {
     std::memset(&P, 0, sizeof P);
     P.state = state;
+    P.state_out = state_out;
     P.ops = fp.d_ops;
     P.n_segs = (uint32_t)fp.segs.size();
     P.n_ops = (uint32_t)fp.ops.size();
@@ -1263,10 +1264,12 @@ static int shard_cut(int n, const FusedPass& fp, int rank, int g, ShardCut& cut)
     return AQS_OK;
 }
 
-static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, const ShardCut* cut = nullptr) {
+// `load_base`: where the pass READS the state (nullptr: in place).  Staged passes of sharded runs read a view of the
+// state in which the peers' parts are local copies, and write the real thing.
+static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, const ShardCut* cut = nullptr, float2* load_base = nullptr) {
     if (fp.n_tiles > 0x7fffffffull) return fail(AQS_ERR_INVALID, "grid too large");
     PassParams P;
-    fill_params(P, state, fp);
+    fill_params(P, load_base ? load_base : state, state, fp);
     uint64_t n_tiles = fp.n_tiles;
     if (cut && cut->fix_n) {        // sharded run: 1 / 2^g of the tiles
         P.fix_n = cut->fix_n;
@@ -1275,7 +1278,7 @@ static int launch_pass(float2* state, const FusedPass& fp, cudaStream_t st, cons
         n_tiles >>= cut->fix_n;
     }
     if (fp.spec && spec_ready(fp)) {
-        int rc = spec_launch(fp, state, n_tiles, P.fix_n, P.fix_or, P.fix_pos, st);
+        int rc = spec_launch(fp, P.state, P.state_out, n_tiles, P.fix_n, P.fix_or, P.fix_pos, st);
         if (rc) return rc;
         count_launch(1);
         return AQS_OK;
@@ -1460,6 +1463,42 @@ int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t first, uint64_t cou
         if (rc) return rc;
     }
     if (first == 0) count_ops(p->ops.size());
+    return AQS_OK;
+}
+
+// One fused pass restricted to the tiles whose number has the bits fix_pos[0 .. fix_n) (ascending positions in the compact
+// tile-number space, cf. aqs_plan_shard_cut) equal to those of fix_or, reading the state at `load_base` (nullptr: in place)
+// and writing it in place, on `stream` (nullptr: the state's own).  This is what a STAGED pass of a sharded run is made
+// of (sharded.py): the tiles of a rank are cut into chunks, each chunk's remote inputs are copied into local staging
+// memory by the copy engines while the previous chunk computes, and the kernel writes its results straight to the peers.
+int aqs_plan_run_tiles(aqs_state_t s, aqs_plan_t p, uint64_t index, const void* load_base, uint32_t fix_n, const uint8_t* fix_pos, uint32_t fix_or,
+                       void* stream) {
+    if (!s || !p) return fail(AQS_ERR_INVALID, "null handle");
+    if (s->n != p->n) return fail(AQS_ERR_INVALID, "plan and state have different qubit counts");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    if (fix_n > 8 || (fix_n && !fix_pos)) return fail(AQS_ERR_INVALID, "at most 8 pinned tile-number bits");
+    const FusedPass& fp = p->passes[index];
+    if ((int)fix_n > p->n - fp.T) return fail(AQS_ERR_INVALID, "more pinned bits than the tile number has");
+    int up = ensure_uploaded(p);
+    if (up) return up;
+    p->ran = true;
+    ShardCut cut;
+    cut.fix_n = fix_n;
+    cut.fix_or = fix_or;
+    for (uint32_t i = 0; i < fix_n; ++i) {
+        if (fix_pos[i] >= p->n - fp.T || (i && fix_pos[i] <= fix_pos[i - 1])) return fail(AQS_ERR_INVALID, "pinned positions must ascend inside the tile number");
+        cut.fix_pos[i] = fix_pos[i];
+    }
+    return launch_pass(s->d, fp, stream ? (cudaStream_t)stream : s->stream, &cut, (float2*)load_base);
+}
+
+// the index-bit positions of the tile of fused pass `index`, ascending (pos has room for 16 entries)
+int aqs_plan_pass_tile(aqs_plan_t p, uint64_t index, uint8_t* pos, int* tile_bits) {
+    if (!p || !pos || !tile_bits) return fail(AQS_ERR_INVALID, "null argument");
+    if (index >= p->passes.size()) return fail(AQS_ERR_INVALID, "pass index out of range");
+    const FusedPass& fp = p->passes[index];
+    *tile_bits = fp.tile.n;
+    for (int j = 0; j < fp.tile.n && j < 16; ++j) pos[j] = fp.tile.pos[j];
     return AQS_OK;
 }
 

@@ -41,8 +41,8 @@ struct SpecSource {
 bool spec_generate(int n, const FusedPass& fp, SpecSource& out, std::string& why_not);
 int spec_attach(int n, std::vector<FusedPass>& passes, bool wait);     // look up / enqueue kernels for every pass
 bool spec_ready(const FusedPass& fp);                                       // kernel compiled and loaded on the current device?
-int spec_launch(const FusedPass& fp, float2* state, uint64_t n_ctas, uint32_t fix_n, uint32_t fix_or, const uint8_t* fix_pos,
-                cudaStream_t st);
+int spec_launch(const FusedPass& fp, float2* state, float2* state_out, uint64_t n_ctas, uint32_t fix_n, uint32_t fix_or,
+                const uint8_t* fix_pos, cudaStream_t st);
 int spec_wait_all();                                                    // block until every queued compilation has finished
 void spec_stats(uint64_t* compiled, uint64_t* cache_hits, uint64_t* failed, double* compile_seconds, uint64_t* pending);
 

@@ -712,7 +712,7 @@ struct Gen {
             }
         }
         auto io_base = [&](const char* name, const uint64_t* toff) {
-            P("  u64* %s = rt.state + (gbase | (u64)(TID & 31u)", name);
+            P("  u64* %s = %s + (gbase | (u64)(TID & 31u)", name, std::strcmp(name, "dst") == 0 ? "rt.state_out" : "rt.state");
             for (int j = kLaneBits; j < TB; ++j) P(" | ((u64)((TID >> %d) & 1u) << %d)", j, __builtin_ctzll(toff[j]));
             P(");\n");
         };
@@ -787,7 +787,7 @@ bool spec_generate(int n, const FusedPass& fp, SpecSource& out, std::string& why
     if (!g.run(why_not)) return false;
     const int NT = 1 << (fp.T - kRegBits);
     const size_t nc = g.coefs.empty() ? 1 : g.coefs.size();
-    if (24 + nc * 8 > 32000) { why_not = "coefficient table exceeds the kernel parameter space"; return false; }
+    if (32 + nc * 8 > 32000) { why_not = "coefficient table exceeds the kernel parameter space"; return false; }
     // The coefficients are individual 64-bit kernel parameters (constant bank -> uniform registers).  One by-value
     // struct holding the table compiles two orders of magnitude slower (measured: cicc 92 s against 2 s for a 388-entry table).
     std::string head;
@@ -795,7 +795,7 @@ bool spec_generate(int n, const FusedPass& fp, SpecSource& out, std::string& why
         char buf[512];
         snprintf(buf, sizeof buf,
                  "#define AQS_NT %d\n#define AQS_NC %zu\n#define AQS_SLOTS %u\n"
-                 "struct RT { u64* state; u32 fix_n, fix_or; unsigned char fix_pos[8]; };\n"
+                 "struct RT { u64* state; u64* state_out; u32 fix_n, fix_or; unsigned char fix_pos[8]; };\n"
                  "#ifdef AQS_HOST_EMU\n"
                  "#define SYNC() pthread_barrier_wait(bar)\n"
                  "static void aqs_pass_body(const RT& rt, const u64* cc, const u32 TID, const u32 BID, u64* sm, pthread_barrier_t* bar) {\n",
@@ -813,7 +813,7 @@ bool spec_generate(int n, const FusedPass& fp, SpecSource& out, std::string& why
         "}\n"
         "#ifdef AQS_HOST_EMU\n"
         "extern \"C\" void aqs_pass_emu_run(u64* state, const u64* coefs, u32 n_ctas, u32 fix_n, u32 fix_or, const unsigned char* fix_pos) {\n"
-        "  RT rt; rt.state = state; rt.fix_n = fix_n; rt.fix_or = fix_or;\n"
+        "  RT rt; rt.state = state; rt.state_out = state; rt.fix_n = fix_n; rt.fix_or = fix_or;\n"
         "  for (int i = 0; i < 8; ++i) rt.fix_pos[i] = fix_pos ? fix_pos[i] : 0;\n"
         "  std::vector<u64> sm(AQS_SLOTS);\n"
         "  for (u32 b = 0; b < n_ctas; ++b) {\n"
@@ -1145,14 +1145,16 @@ bool spec_ready(const FusedPass& fp) {
     return true;
 }
 
-int spec_launch(const FusedPass& fp, float2* state, uint64_t n_ctas, uint32_t fix_n, uint32_t fix_or, const uint8_t* fix_pos, cudaStream_t st) {
+int spec_launch(const FusedPass& fp, float2* state, float2* state_out, uint64_t n_ctas, uint32_t fix_n, uint32_t fix_or, const uint8_t* fix_pos,
+                cudaStream_t st) {
     const SpecKernel* k = fp.spec.get();
-    // parameters: RT { u64* state; u32 fix_n, fix_or; u8 fix_pos[8]; }, then one u64 per coefficient
-    uint64_t rt[3];
+    // parameters: RT { u64* state; u64* state_out; u32 fix_n, fix_or; u8 fix_pos[8]; }, then one u64 per coefficient
+    uint64_t rt[4];
     rt[0] = (uint64_t)(uintptr_t)state;
-    rt[1] = (uint64_t)fix_n | ((uint64_t)fix_or << 32);
-    rt[2] = 0;
-    if (fix_pos) std::memcpy(&rt[2], fix_pos, 8);
+    rt[1] = (uint64_t)(uintptr_t)state_out;
+    rt[2] = (uint64_t)fix_n | ((uint64_t)fix_or << 32);
+    rt[3] = 0;
+    if (fix_pos) std::memcpy(&rt[3], fix_pos, 8);
     std::vector<void*> argv(1 + fp.spec_coefs.size());
     argv[0] = rt;
     for (size_t i = 0; i < fp.spec_coefs.size(); ++i) argv[1 + i] = const_cast<uint64_t*>(&fp.spec_coefs[i]);

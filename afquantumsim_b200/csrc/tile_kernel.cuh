@@ -153,7 +153,8 @@ static_assert(sizeof(DevOp) == 64, "DevOp layout");
 constexpr uint32_t kDevOpEnd = 0x3fu;   // group value of the sentinel that follows the last op
 
 struct alignas(16) PassParams {
-    float2* state;
+    float2* state;         // loads
+    float2* state_out;     // stores (== state, except for staged passes of sharded runs: flat.cu)
     const DevOp* ops;      // n_ops + 1 entries (sentinel), global memory
     uint32_t n_segs;
     uint32_t n_ops;
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(1 << (T - kRegBits), tile_min_blocks(T)) k_til
 #pragma unroll
         for (int j = kLaneBits; j < TB; ++j)
             if (tid >> j & 1u) g += P.st_toff[j];
-        float2* dst = P.state + g;
+        float2* dst = P.state_out + g;
         const bool sc = P.has_scale != 0;
         const f2 re = bc(P.scale.x);
         const f2 im = pk(-P.scale.y, P.scale.y);

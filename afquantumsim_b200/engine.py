@@ -65,6 +65,7 @@ ABI_SYMBOLS = [
     "aqs_apply_dense", "aqs_flat_create", "aqs_flat_attach", "aqs_flat_ptr", "aqs_flat_destroy", "aqs_plan_run_shard", "aqs_plan_pass_span", "aqs_plan_shard_cut",
     "aqs_plan_pass_source", "aqs_plan_pass_coefs", "aqs_plan_jit_ready", "aqs_jit_wait", "aqs_jit_get_info",
     "aqs_sample_hist_sparse", "aqs_pool_trim",
+    "aqs_flat_view_create", "aqs_memcpy_async", "aqs_plan_run_tiles", "aqs_plan_pass_tile",
 ]
 
 
@@ -108,6 +109,9 @@ def load():
         "aqs_plan_pass_source": [vp, u64, vp, u64, P(u64), P(u64)], "aqs_plan_pass_coefs": [vp, u64, vp, u64, P(u64)],
         "aqs_plan_jit_ready": [vp, P(u64)], "aqs_jit_wait": [], "aqs_jit_get_info": [P(JitInfo)],
         "aqs_sample_hist_sparse": [vp, vp, u64, vp, vp, u64, P(u64)], "aqs_pool_trim": [],
+        "aqs_plan_pass_tile": [vp, u64, P(ctypes.c_uint8), P(i32)],
+        "aqs_flat_view_create": [vp, vp, u64, P(vp)], "aqs_memcpy_async": [vp, vp, u64, vp],
+        "aqs_plan_run_tiles": [vp, vp, u64, vp, ctypes.c_uint32, P(ctypes.c_uint8), ctypes.c_uint32, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -201,6 +205,7 @@ class FlatSpace:
         fd = ctypes.c_int(-1)
         _check(load().aqs_flat_create(shard_bytes, world, rank, ctypes.byref(self._h), ctypes.byref(fd)))
         self.fd = fd.value          # POSIX handle of this rank's shard, to be passed to the other processes
+        self._views = {}            # views of the state for staged passes, by their block lists (sharded.py)
 
     def attach(self, peer_rank: int, fd: int):
         _check(load().aqs_flat_attach(self._h, peer_rank, fd))
@@ -209,6 +214,14 @@ class FlatSpace:
         base, own = ctypes.c_void_p(), ctypes.c_void_p()
         _check(load().aqs_flat_ptr(self._h, ctypes.byref(base), ctypes.byref(own)))
         return base.value, own.value
+
+    def view(self, blocks) -> int:
+        """Base of a view of the state: own shard as usual, the listed (state_offset, bytes) blocks of peer shards backed
+        by local staging memory, everything else unmapped."""
+        arr = np.ascontiguousarray(np.asarray(blocks, dtype=np.uint64).reshape(-1, 2))
+        p = ctypes.c_void_p()
+        _check(load().aqs_flat_view_create(self._h, arr.ctypes.data_as(ctypes.c_void_p), len(arr), ctypes.byref(p)))
+        return p.value
 
     def close(self):
         if getattr(self, "_h", None):
@@ -242,6 +255,13 @@ class Plan:
         v = ctypes.c_int()
         _check(load().aqs_plan_pass_span(self._h, index, log2_world, ctypes.byref(v)))
         return v.value
+
+    def pass_tile(self, index: int):
+        """Index-bit positions of the tile of fused pass `index`, ascending."""
+        pos = (ctypes.c_uint8 * 16)()
+        t = ctypes.c_int()
+        _check(load().aqs_plan_pass_tile(self._h, index, pos, ctypes.byref(t)))
+        return [int(pos[j]) for j in range(t.value)]
 
     def shard_cut(self, index: int, rank: int, log2_world: int):
         """(positions, value): rank `rank` runs the tiles of pass `index` whose number has these bits at this value."""
@@ -430,6 +450,13 @@ class State:
     def run(self, plan: Plan):
         _check(load().aqs_plan_run(self._h, plan._h))
 
+    def run_tiles(self, plan: Plan, index: int, load_base: int, fix_pos, fix_or: int, stream: int = 0):
+        """One fused pass on the tiles whose number has the bits `fix_pos` pinned to those of `fix_or`, reading the state at
+        `load_base` (0: in place), writing in place, on CUDA stream `stream` (0: the state's own)."""
+        pos = (ctypes.c_uint8 * 8)(*fix_pos)
+        _check(load().aqs_plan_run_tiles(self._h, plan._h, index, ctypes.c_void_p(load_base or None), len(fix_pos), pos, fix_or,
+                                         ctypes.c_void_p(stream or None)))
+
     def run_shard(self, plan: Plan, first: int, count: int, rank: int, log2_world: int):
         """This rank's share of passes [first, first + count) on a flat multi-GPU state (aqs_plan_run_shard)."""
         _check(load().aqs_plan_run_shard(self._h, plan._h, first, count, rank, log2_world))
@@ -493,6 +520,10 @@ class State:
         _check(load().aqs_sample_hist_sparse(self._h, u.ctypes.data_as(ctypes.c_void_p), u.size, idx.ctypes.data_as(ctypes.c_void_p),
                                              cnt.ctypes.data_as(ctypes.c_void_p), idx.size, ctypes.byref(bins)))
         return idx[:bins.value].copy(), cnt[:bins.value].copy()
+
+
+def memcpy_async(dst: int, src: int, nbytes: int, stream: int) -> None:
+    _check(load().aqs_memcpy_async(ctypes.c_void_p(dst), ctypes.c_void_p(src), nbytes, ctypes.c_void_p(stream or None)))
 
 
 def pool_trim() -> None:

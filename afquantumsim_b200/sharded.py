@@ -123,7 +123,7 @@ class _Sched:
         if self.pending:
             st = self.st
             ops = np.concatenate(self.pending)
-            flags = (eng.PLAN_FUSE | st._jit_flags(self.wait)) if st.fuse else 0
+            flags = (eng.PLAN_FUSE | (st._jit_flags(self.wait) if self.wait is not None else 0)) if st.fuse else 0
             self.steps.append(("plan", eng.Plan(st.n_local, ops, flags), len(ops)))
             self.pending = []
 
@@ -194,6 +194,7 @@ class ShardedState:
         self.fuse = fuse
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_plans": 0, "local_ops": 0, "local_swaps": 0}
         self.stage = None           # half-shard staging buffer of the NCCL path, made on first use
+        self._copy_stream = None    # staged passes: the stream the copy engines work on
         self.p2p = False
         self.peer_ptrs: List[int] = []
         self.flat = None            # eng.FlatSpace: every shard of the node in one virtual address range
@@ -268,6 +269,10 @@ class ShardedState:
         self.state.set_stream(stream)
         self.flat_state.set_stream(stream)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # every shard is addressable through the flat range: the in-place remap kernel (aqs_peer_bitswap) needs no CUDA IPC
+        shard_bytes = 8 << self.n_local
+        self.peer_ptrs = [base + r * shard_bytes for r in range(self.world)]
+        self.p2p = True
         return True
 
     def close(self):
@@ -452,19 +457,61 @@ class ShardedState:
         layout: everything executable between two remaps becomes one fused local plan.  On a flat
         address space there is nothing to schedule: ONE fused plan over all n qubits, no remaps."""
         if self.flat_state is not None:
-            recs = np.ascontiguousarray(records, dtype=eng.OP_DTYPE)
+            # Two schedules exist on a flat address space.  "flat": ONE fused plan over all n qubits, passes whose tiles
+            # hold rank bits move their remote part over NVLink — there and back, every such pass.  "remap": lazy global
+            # qubit swaps (one in-place exchange moves half a shard once, the qubit then stays local) around fused LOCAL
+            # plans.  Which one moves fewer bytes depends on the circuit (brickwork-32, depth 20 on 2 GPUs: 48 GiB per
+            # direction against 8), so both are planned — without their kernels, that takes milliseconds — and priced.
+            mode = os.environ.get("AQS_SHARD_SCHEDULE", "auto")
+            cands = {}
+            canonical = self.pos == [self.n - 1 - q for q in range(self.n)]      # (the whole-state plan assumes it)
+            if mode in ("auto", "flat") and canonical:
+                cands["flat"] = self._compile_flat(records, 0, stage=False)
+            if mode in ("auto", "remap") or not cands:
+                cands["remap"] = self._compile_remap(records, None)
+            shard_bytes = 8 << self.n_local
+
+            def cost(pl):      # seconds: streaming passes over the shard + NVLink bytes per direction (reads and the peers' writes)
+                return pl.n_passes * 2.0 * shard_bytes / 4.5e12 + 2.0 * pl.exchange_bytes / 0.7e12
+
+            pick = min(cands, key=lambda k: cost(cands[k]))
+            self.stats["schedule"] = pick
+            jit = self._jit_flags(wait)
+            if not jit:
+                return cands[pick]
+            del cands
+            return self._compile_flat(records, jit) if pick == "flat" else self._compile_remap(records, wait)
+        return self._compile_remap(records, wait)
+
+    def _compile_flat(self, records: np.ndarray, jit_flags: int, stage: bool = True) -> ShardedPlan:
+        recs = np.ascontiguousarray(records, dtype=eng.OP_DTYPE)
+        if True:
             plan = ShardedPlan([], self.pos, self.pos)
             if len(recs):
-                ep = eng.Plan(self.n, recs, eng.PLAN_FUSE | self._jit_flags(wait))
+                ep = eng.Plan(self.n, recs, eng.PLAN_FUSE | jit_flags)
                 n_passes = int(ep.info()["n_fused_passes"])
                 spans = [ep.pass_span(i, self.g) for i in range(n_passes)]
-                plan.steps.append(("flat", ep, spans, len(recs)))
+                # spanning passes run STAGED where their geometry allows (bulk copies of the peers' blocks into local
+                # staging memory, pipelined with the kernel; AQS_STAGED=0 reads the peers from inside the kernel instead)
+                staged = {}
+                if stage and os.environ.get("AQS_STAGED", "1") != "0":
+                    for i, j in enumerate(spans):
+                        geo = self._stage_pass(ep, i) if j else None
+                        if geo is not None:
+                            key = tuple(geo[0])
+                            if key not in self.flat._views:
+                                self.flat._views[key] = self.flat.view(geo[0])
+                            staged[i] = (self.flat._views[key], geo[1])
+                plan.steps.append(("flat", ep, spans, len(recs), staged))
                 plan.n_local_ops, plan.n_passes = len(recs), n_passes
                 # NVLink bytes this rank writes: in a pass whose tile holds j rank bits, (2^j - 1) / 2^j of the
                 # amplitudes it processes (one shard's worth) live on peers
                 plan.n_exchanges = sum(1 for j in spans if j)
                 plan.exchange_bytes = sum((8 << self.n_local) * ((1 << j) - 1) // (1 << j) for j in spans)
             return plan
+
+    def _compile_remap(self, records: np.ndarray, wait) -> ShardedPlan:
+        """wait: True / False = fused local plans with specialised kernels (waiting for them or not), None = without"""
         sch = _Sched(self, wait)
         pos = sch.pos
         remaining = [_Op(r) for r in np.ascontiguousarray(records, dtype=eng.OP_DTYPE)]
@@ -522,7 +569,7 @@ class ShardedState:
             elif step[0] == "p2p":
                 self._p2p_swap(step[1], step[2])
             elif step[0] == "flat":
-                self._run_flat(step[1], step[2])
+                self._run_flat(step[1], step[2], step[4])
                 self.stats["local_plans"] += 1
                 self.stats["local_ops"] += step[3]
             else:
@@ -531,7 +578,102 @@ class ShardedState:
         self.stats["exchanges"] += plan.n_exchanges
         self.stats["exchange_bytes"] += plan.exchange_bytes
 
-    def _run_flat(self, plan: "eng.Plan", spans: Sequence[int]):
+    # ------------------------------------------------------------------ staged passes
+    def _stage_pass(self, ep: "eng.Plan", i: int, max_chunk_bits: int = 3):
+        """Geometry of a STAGED run of spanning pass i (engine: flat.cu).  The tiles this rank runs are those whose
+        pinned bits (aqs_plan_shard_cut) match the rank; the peers' amplitudes they need form, in every involved peer
+        shard, the set { local index x : x[b] = v_b for the pinned spare bits b } — large contiguous blocks.  The pass
+        is cut into chunks by pinning up to three more high local bits.  Returns (view blocks, chunks) with
+        chunks = [(copies, fix_pos, fix_or)], copies = [(state byte offset, bytes)], or None when
+        the blocks would be smaller than the 2 MiB mapping granularity (the pass then reads its peers directly)."""
+        n, nl, g, rank = self.n, self.n_local, self.g, self.rank
+        tile = set(ep.pass_tile(i))
+        nontile = [b for b in range(n) if b not in tile]              # compact tile-number position c <-> index bit nontile[c]
+        fix_pos, fix_or = ep.shard_cut(i, rank, g)
+        pinned = {nontile[c]: (fix_or >> c) & 1 for c in fix_pos}
+        spare = {b: v for b, v in pinned.items() if b < nl}           # local bits pinned because a rank bit sits in the tile
+        in_tile_rank = [b for b in range(nl, n) if b in tile]
+        if not in_tile_rank or len(spare) != len(in_tile_rank):
+            return None
+        free_hi = [b for b in range(nl - 1, -1, -1) if b not in tile and b not in pinned]
+        gran_amps = (2 << 20) // 8
+        chunk_bits = []
+        for b in free_hi[:max_chunk_bits]:
+            if (1 << min([b] + list(spare))) >= gran_amps:
+                chunk_bits.append(b)
+        lowest = min(list(spare) + chunk_bits)
+        if (1 << lowest) < gran_amps:
+            return None
+        fixed_bits = sorted(list(spare) + chunk_bits)
+        free_above = [b for b in range(lowest + 1, nl) if b not in fixed_bits]
+        if len(free_above) > 10:
+            return None
+        peers = []
+        for v in range(1 << len(in_tile_rank)):
+            s_ = rank
+            for k, b in enumerate(in_tile_rank):
+                s_ = (s_ & ~(1 << (b - nl))) | (((v >> k) & 1) << (b - nl))
+            if s_ != rank:
+                peers.append(s_)
+        shard_bytes = 8 << nl
+        blocks, chunks, staged_bytes = [], [], 0
+        for cv in range(1 << len(chunk_bits)):
+            vals = dict(spare)
+            for k, b in enumerate(chunk_bits):
+                vals[b] = (cv >> k) & 1
+            base = sum(v << b for b, v in vals.items())
+            copies = []
+            for fa in range(1 << len(free_above)):
+                start = base + sum(((fa >> k) & 1) << b for k, b in enumerate(free_above))
+                for s_ in peers:
+                    state_off = s_ * shard_bytes + start * 8
+                    blocks.append((state_off, 8 << lowest))
+                    copies.append((state_off, 8 << lowest))
+                    staged_bytes += 8 << lowest
+            # the launch: the rank's pinned bits plus this chunk's
+            pos = dict(pinned)
+            for k, b in enumerate(chunk_bits):
+                pos[b] = (cv >> k) & 1
+            cpos = sorted(nontile.index(b) for b in pos)
+            cor = sum(pos[nontile[c]] << c for c in cpos)
+            chunks.append((copies, cpos, cor))
+        assert staged_bytes <= shard_bytes
+        return blocks, chunks
+
+    def _run_staged(self, ep: "eng.Plan", i: int, staged):
+        """One spanning pass, staged: the copy engines fetch chunk c + 1's remote blocks while chunk c computes."""
+        view, chunks = staged
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        base, _ = self.flat.pointers()
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        cs.wait_event(ev0)                      # (after the barrier: every peer has finished the previous pass)
+        events = []
+        exp = os.environ.get("AQS_STAGED_EXP", "")          # (dev experiments: timing of the parts; results are wrong)
+        for copies, _, _ in chunks:
+            for po, nb in copies:
+                if exp not in ("nocopy", "nocopy_localstore"):
+                    eng.memcpy_async(view + po, base + po, nb, cs.cuda_stream)       # peer HBM -> the view's local backing
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            events.append(ev)
+        target = self.flat_state
+        if exp in ("localstore", "nocopy_localstore"):
+            if not hasattr(self, "_exp_state"):
+                self._exp_state = {}
+            if view not in self._exp_state:
+                self._exp_state[view] = eng.State.wrap(self.n, view)
+                self._exp_state[view].set_stream(main.cuda_stream)
+            target = self._exp_state[view]
+        for (copies, cpos, cor), ev in zip(chunks, events):
+            main.wait_event(ev)
+            if exp != "nokernel":
+                target.run_tiles(ep, i, view, cpos, cor)
+
+    def _run_flat(self, plan: "eng.Plan", spans: Sequence[int], staged=None):
         """This rank's share of every pass of a whole-state fused plan.  A pass whose tile holds no rank
         bit touches only this rank's shard; one that does reads and writes peer memory over NVLink, so a
         stream-ordered barrier separates it from its neighbours (all of it asynchronous on the stream)."""
@@ -539,7 +681,10 @@ class ShardedState:
         while i < n:
             if spans[i]:
                 self._stream_barrier()
-                self.flat_state.run_shard(plan, i, 1, self.rank, self.g)
+                if staged is not None and staged.get(i) is not None:
+                    self._run_staged(plan, i, staged[i])
+                else:
+                    self.flat_state.run_shard(plan, i, 1, self.rank, self.g)
                 dirty = True
                 i += 1
             else:

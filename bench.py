@@ -499,12 +499,15 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
-def sharded_parity(ShardedState, orc, wl, torch, dist, rank, world, g):
+def sharded_parity(ShardedState, orc, wl, torch, dist, rank, world, g, jit):
     """Before timing: the data path of this run (flat address space where available) against the unsharded CPU oracle."""
     n = 22 + g
     gates = wl.brickwork(n, 8)
-    st = ShardedState(n)
-    st.apply_ops(wl.to_ops(gates))
+    st = ShardedState(n, jit=jit)
+    plan = st.compile(wl.to_ops(gates))          # (waits for the specialised kernels: the path that is timed below)
+    st.run(plan)
+    jit_passes, passes = plan.jit_ready(), plan.n_passes
+    del plan
     u = np.random.default_rng(5).random(500, dtype=np.float32)
     out = st.sample(u)
     full = st.gather()
@@ -512,8 +515,9 @@ def sharded_parity(ShardedState, orc, wl, torch, dist, rank, world, g):
     if rank == 0:
         want = orc.simulate(orc.new_state(n), orc.Circ(n, gates))
         res[0] = {"n": n, "gates": len(gates), "rel_l2": orc.rel_l2(full, want),
-                  "sampling_bit_identical_to_oracle": bool(np.array_equal(out, orc.sample(want, u, "exact"))),
-                  "flat_address_space": st.flat_state is not None, "world": world}
+                  "sampling_bit_identical_to_oracle": bool(np.array_equal(out, orc.sample(full, u, "exact"))),   # same state, same draws
+                  "flat_address_space": st.flat_state is not None, "world": world,
+                  "path": f"{jit_passes} of {passes} passes on specialised kernels"}
     dist.broadcast_object_list(res, src=0)
     st.close()
     del st
@@ -537,7 +541,7 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
         dist.barrier()
         torch.cuda.synchronize()
 
-    parity = sharded_parity(ShardedState, orc, wl, torch, dist, rank, world, g)
+    parity = sharded_parity(ShardedState, orc, wl, torch, dist, rank, world, g, not args.no_jit)
     eng.pool_trim()
     st = ShardedState(n, jit=not args.no_jit)
 
@@ -579,8 +583,9 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
     assert abs(norm2 - 1.0) < 1e-3, f"state norm drifted: {norm2}"
     remap_p2p, plan_passes, plan_local_ops = bool(st.p2p), plan.n_passes, plan.n_local_ops
     flat_mode = st.flat_state is not None
-    jit_passes = plan.jit_ready() if flat_mode else 0
-    spans = plan.spans() if flat_mode else []
+    schedule = st.stats.get("schedule") or ("remap" if not flat_mode else "flat")
+    jit_passes = plan.jit_ready()
+    spans = plan.spans() if schedule == "flat" else []
     del plan
 
     # e2e: host-built gate list -> ops -> sharded simulate -> 1000-draw sample read back, every step
@@ -624,10 +629,13 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
             "workload": (f"brickwork-{n} depth {args.depth}" if args.workload == "brickwork" else f"fourier_transform({n})")
                         + f": {gate_apps} gate applications on ONE 2^{n} state; {S_shard / 2**30:.0f} GiB shard per GPU",
             "parallelism": f"state sharded over {world} GPUs on the top {g} qubits; "
-                           + ("all shards in one flat NVLink address space: one fused plan over the whole state, each GPU runs "
-                              "1/N of the tiles of every pass, tiles that contain rank bits load/store peer memory" if flat_mode
-                              else "global-qubit remaps " + ("in place over NVLink peer memory (aqs_peer_bitswap)" if remap_p2p
-                                                            else "as half-shard NCCL send/recv")),
+                           + ("all shards mapped into one flat NVLink address space (CUDA VMM); " if flat_mode else "")
+                           + ("schedule 'flat': one fused plan over the whole state, each GPU runs 1/N of the tiles of every pass, tiles that "
+                              "contain rank bits move their remote part over NVLink (staged through the copy engines, written back from the kernel)"
+                              if schedule == "flat" else
+                              "schedule 'remap': lazy global-qubit swaps around fused local plans, " +
+                              ("each swap one in-place exchange kernel over peer memory (aqs_peer_bitswap)" if remap_p2p else "each swap a half-shard NCCL send/recv"))
+                           + "; both schedules are planned and the one that moves fewer bytes runs",
             "fusion": "on", "jit": f"{jit_passes} of {plan_passes} passes on specialised kernels (compiled in {build_s:.2f} s)",
             "l2": f"shard is {S_shard / 2**30:.0f} GiB >> 126 MB L2",
         },
@@ -641,6 +649,7 @@ def run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local):
         "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
         "clocks": clocks,
         "exchange": {"per_step": exchanges, "bytes_per_rank_per_step": xbytes, "peer_memory": remap_p2p or flat_mode, "flat_address_space": flat_mode,
+                     "schedule": schedule,
                      "local_passes_per_step": plan_passes, "local_ops_per_step": plan_local_ops, "rank_bits_per_pass": spans,
                      "note": "bytes each rank writes to its peers over NVLink per step (it reads as many)"},
         "roofline": {"bound": "hbm", "achieved": plan_passes * 2.0 * S_shard / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

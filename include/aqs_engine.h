@@ -257,9 +257,22 @@ int aqs_flat_ptr(aqs_flat_t f, void** base, void** own_shard);
 int aqs_flat_destroy(aqs_flat_t f);
 int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t first, uint64_t count, int rank, int log2_world);
 int aqs_plan_pass_span(aqs_plan_t p, uint64_t index, int log2_world, int* rank_bits_in_tile);
+/* the index-bit positions of the tile of fused pass `index`, ascending (pos: 16 entries of storage) */
+int aqs_plan_pass_tile(aqs_plan_t p, uint64_t index, uint8_t* pos, int* tile_bits);
 /* introspection (tests): which tiles of pass `index` rank `rank` runs — the tile numbers whose bits
  * fix_pos[0 .. *fix_n) (ascending, 8 entries of storage) equal those of *fix_or */
 int aqs_plan_shard_cut(aqs_plan_t p, uint64_t index, int rank, int log2_world, uint32_t* fix_n, uint32_t* fix_or, uint8_t* fix_pos);
+/* Staged passes (flat.cu, sharded.py).  Scattered 256-byte reads of peer HBM run at about half the NVLink rate, large
+ * contiguous copies and peer writes at the full rate, so a pass whose tiles contain rank bits is run in CHUNKS of tiles:
+ * the copy engines fetch the next chunk's remote blocks into local staging memory (aqs_memcpy_async, to the view's own
+ * addresses) while the kernel computes the current chunk, reading a VIEW of the state in which those blocks are backed by
+ * local staging allocations (aqs_flat_view_create) and writing its results directly into the peers' HBM (aqs_plan_run_tiles: one pass,
+ * restricted to the tiles whose number has the listed bits pinned, loads from `load_base`, stores in place). */
+typedef struct aqs_flat_block { uint64_t state_offset, bytes; } aqs_flat_block;   /* in bytes; multiples of the 2 MiB mapping granularity */
+int aqs_flat_view_create(aqs_flat_t f, const aqs_flat_block* blocks, uint64_t n_blocks, void** view_base);
+int aqs_memcpy_async(void* dst, const void* src, uint64_t bytes, void* stream);
+int aqs_plan_run_tiles(aqs_state_t s, aqs_plan_t p, uint64_t index, const void* load_base, uint32_t fix_n, const uint8_t* fix_pos,
+                       uint32_t fix_or, void* stream);
 
 /* ---- timing (CUDA events on the state's stream) ---------------------------- */
 int aqs_timer_create(aqs_timer_t* out);

@@ -290,6 +290,12 @@ int aqs_flat_create(uint64_t b, int w, int r, aqs_flat_t* o, int* fd) { (void)b;
 int aqs_flat_attach(aqs_flat_t f, int r, int fd) { (void)f; (void)r; (void)fd; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
 int aqs_flat_ptr(aqs_flat_t f, void** b, void** o) { (void)f; (void)b; (void)o; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
 int aqs_flat_destroy(aqs_flat_t f) { (void)f; return AQS_OK; }
+int aqs_plan_pass_tile(aqs_plan_t p, uint64_t i, uint8_t* pos, int* t) { (void)p; (void)i; (void)pos; (void)t; return fail(AQS_ERR_STATE, "no fused passes on the cpu shim"); }
+int aqs_flat_view_create(aqs_flat_t f, const aqs_flat_block* b, uint64_t n, void** v) { (void)f; (void)b; (void)n; (void)v; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
+int aqs_memcpy_async(void* d, const void* s, uint64_t b, void* st) { (void)d; (void)s; (void)b; (void)st; return fail(AQS_ERR_STATE, "no device memory on the cpu shim"); }
+int aqs_plan_run_tiles(aqs_state_t s, aqs_plan_t p, uint64_t i, const void* l, uint32_t n, const uint8_t* fp, uint32_t fo, void* st) {
+    (void)s; (void)p; (void)i; (void)l; (void)n; (void)fp; (void)fo; (void)st; return fail(AQS_ERR_STATE, "no fused passes on the cpu shim");
+}
 int aqs_plan_run_shard(aqs_state_t s, aqs_plan_t p, uint64_t a, uint64_t c, int r, int g) { (void)s; (void)p; (void)a; (void)c; (void)r; (void)g; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
 int aqs_plan_shard_cut(aqs_plan_t p, uint64_t i, int r, int g, uint32_t* n, uint32_t* v, uint8_t* pos) { (void)p; (void)i; (void)r; (void)g; (void)n; (void)v; (void)pos; return fail(AQS_ERR_STATE, "no flat address space on the cpu shim"); }
 int aqs_plan_pass_span(aqs_plan_t p, uint64_t i, int g, int* out) { (void)p; (void)i; (void)g; if (out) *out = 0; return AQS_OK; }
