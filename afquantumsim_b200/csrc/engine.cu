@@ -832,9 +832,8 @@ int aqs_peer_bitswap(aqs_state_t s, void* const* members, int k, const int* loca
     A.n_items = s->N >> A.fixed.n;
     const uint64_t per_block = (uint64_t)kPeerThreads * kPeerItems;
     const uint64_t gx = (A.n_items + per_block - 1) / per_block;
-    REQUIRE(gx <= 0x7fffffffull, "grid too large");
-    dim3 grid((unsigned)gx, (1u << k) - 1u);
-    k_peer_bitswap<<<grid, kPeerThreads, 0, s->stream>>>(A);
+    REQUIRE(gx * ((1ull << k) - 1ull) <= 0x7fffffffull, "grid too large");
+    k_peer_bitswap<<<(unsigned)(gx * ((1ull << k) - 1ull)), kPeerThreads, 0, s->stream>>>(A);
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return AQS_OK;
