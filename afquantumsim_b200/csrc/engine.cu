@@ -18,6 +18,7 @@
 #include "measure_kernels.cuh"
 #include "peer_kernels.cuh"
 #include "dense_kernels.cuh"
+#include "dense_tc.cuh"
 
 namespace aqs {
 
@@ -728,6 +729,54 @@ int aqs_apply_dense(aqs_state_t s, const int* qubits, int k, uint64_t ctrl_mask,
     A.ctrl_or = cv;
     bitlist_from_mask(fixedmask | cm, A.fixed);
     A.n_groups = s->N >> A.fixed.n;
+    // ---- tensor-core path (dense_tc.cuh): k = 4, 5, 6 as a 64 x 64 matrix (k < 6: I (x) M on the lowest free index bits,
+    // which also lengthens the contiguous runs), 3xTF32 on tcgen05 with the accumulator in tensor memory
+    {
+        const char* e = std::getenv("AQS_DENSE_TC");
+        const int min_k = e ? (std::atoi(e) > 0 ? std::atoi(e) : 99) : 5;      // AQS_DENSE_TC=0: off; =k: from k qubits on (k = 4: 6.8 ms against 4.4 on the SIMT kernel)
+        const int pad = 6 - k;
+        if (k >= min_k && n - k - __builtin_popcountll(cm) >= pad + 6) {
+            DenseTcArgs T;
+            std::memset(&T, 0, sizeof T);
+            T.a = s->d;
+            T.ctrl_or = cv;
+            for (int i = 0; i < k; ++i) T.toff[i] = A.toff[i];
+            uint64_t allmask = fixedmask | cm;
+            for (int i = k, b = 0; i < 6; ++b)
+                if (!(allmask >> b & 1ull)) { T.toff[i++] = 1ull << b; allmask |= 1ull << b; }
+            bitlist_from_mask(allmask, T.fixed);
+            T.n_groups = s->N >> T.fixed.n;
+            // W' = I (x) M, row-major 64 x 64 complex
+            std::vector<float> w((size_t)64 * 64 * 2, 0.f);
+            for (int sp = 0; sp < (1 << pad); ++sp)
+                for (int r = 0; r < D; ++r)
+                    for (int c = 0; c < D; ++c) {
+                        const size_t idx = ((size_t)((sp << k) | r) * 64 + (size_t)((sp << k) | c)) * 2;
+                        w[idx] = m[r * D + c].re;
+                        w[idx + 1] = m[r * D + c].im;
+                    }
+            const size_t bytes = w.size() * sizeof(float);
+            int rc = ensure_scratch(s, bytes);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s->scratch, w.data(), bytes, cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            count_h2d(bytes);
+            T.m = (const float2*)s->scratch;
+            static bool opted = false;
+            if (!opted) {
+                CUDA_TRY(cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+                opted = true;
+            }
+            const uint64_t tiles = T.n_groups / kTcGroups;
+            const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_sm_count);
+            k_dense_tc<<<grid, kTcThreads, kTcSmemBytes, s->stream>>>(T);
+            cudaError_t e2 = cudaGetLastError();
+            if (e2 != cudaSuccess) return fail_cuda(e2, "tensor-core dense kernel launch", __LINE__);
+            count_launch(1);
+            count_ops(1);
+            return AQS_OK;
+        }
+    }
     // matrix -> device as packed operand pairs {re, re, -im, im}
     std::vector<float> packed((size_t)D * D * 4);
     for (int i = 0; i < D * D; ++i) {
