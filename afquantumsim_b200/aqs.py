@@ -226,6 +226,16 @@ class QCircuit:
             gate._append_to(self)
         return self
 
+    def set_matrix(self, matrix) -> "QCircuit":
+        """Make this gate-less circuit (at most 6 qubits) the opaque matrix `matrix` (2^n x 2^n, matrix[r, c]): what the
+        reference's `qc.circuit() = M` does (docs/USAGE.md:121-125).  Gate / ControlGate of it apply the matrix through the
+        engine's dense-matrix kernel (tensor cores from 5 qubits on)."""
+        m = np.ascontiguousarray(np.asarray(matrix, dtype=np.complex64))
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise InvalidArgument("set_matrix: a square matrix is required")
+        _ck(_load().aqsh_circuit_set_matrix(self._h, m.ctypes.data_as(ctypes.c_void_p), int(m.shape[0])))
+        return self
+
     def copy(self) -> "QCircuit":
         h = ctypes.c_void_p()
         _ck(_load().aqsh_circuit_copy(self._h, ctypes.byref(h)))

@@ -60,9 +60,22 @@ void jit_wait();   /* block until no kernel compilation is pending */
 bool get_fusion();
 
 /* Collects the primitive ops a gate lowers to. */
+/* An opaque 2^k x 2^k matrix on contiguous qubits [begin, begin + k): what Gate / ControlGate apply when the inner
+ * circuit's matrix was written by the user (reference src/quantum.cpp:1760-1814, 1888-1950; docs/USAGE.md:121-125).
+ * It cannot travel in a 64-byte aqs_op record, so the op list carries a marker (kind AQS_HOST_DENSE_MARK, target =
+ * index into the list of these records) and the host layer calls aqs_apply_dense between the fused segments. */
+struct DenseGateRec {
+    uint32_t begin = 0, k = 0;
+    uint64_t ctrl_mask = 0;
+    std::vector<aqs_c32> m;   /* row-major, qubit `begin` = most significant matrix-index bit */
+};
+constexpr int AQS_HOST_DENSE_MARK = 99;
+
 struct OpSink {
     std::vector<aqs_op>* ops;
     uint32_t qubits;
+    std::vector<DenseGateRec>* dense = nullptr;
+    void dense_gate(uint32_t begin, uint32_t k, uint64_t ctrl_mask, const af::array& matrix_colmajor);
     void u2(uint32_t target, const af::cfloat m[4], uint64_t ctrl_mask);
     void diag(uint32_t target, af::cfloat d0, af::cfloat d1, uint64_t ctrl_mask);
     void x(uint32_t target, uint64_t ctrl_mask, uint64_t ctrl_value);
@@ -162,10 +175,17 @@ class QCircuit {
     /* The compiled prefix as a dense column-major 2^n x 2^n matrix.  The reference
      * keeps this matrix eagerly (src/quantum.cpp:159-164); here it is built on
      * demand by running the compiled ops over the columns of I on the device, and
-     * only for n <= 13 (std::length_error beyond).  Writing through the returned
-     * reference does not change the circuit. */
+     * only for n <= 13 (std::length_error beyond).
+     * Write-through: on a circuit WITHOUT gates of at most 6 qubits the non-const accessor returns a matrix the circuit
+     * owns (initially the identity); what the user writes into it is what Gate{circuit, b} / ControlGate{circuit, c, b}
+     * apply (the engine's dense-matrix kernel, aqs_apply_dense), like the reference's `qc.circuit() = M`
+     * (docs/USAGE.md:121-125).  On circuits with gates, writes through the reference do not change the circuit. */
     af::array& circuit();
     const af::array& circuit() const;
+    /* the same, explicitly: make this (gate-less) circuit the opaque matrix m (2^n x 2^n, column-major like af::array) */
+    void set_matrix(const af::array& m);
+    bool opaque() const noexcept { return user_matrix_ != nullptr && gate_list_.empty(); }
+    const af::array* user_matrix() const noexcept { return user_matrix_.get(); }
 
     auto& gate_list() noexcept { return gate_list_; }
     const auto& gate_list() const noexcept { return gate_list_; }
@@ -186,6 +206,11 @@ class QCircuit {
         return *compiled_ops_;
     }
     const std::vector<aqs_op>& compiled_ops() const noexcept { return *compiled_ops_; }
+    std::vector<DenseGateRec>& compiled_dense() {
+        detach();
+        return *compiled_dense_;
+    }
+    const std::vector<DenseGateRec>& compiled_dense() const noexcept { return *compiled_dense_; }
     std::size_t cached_index() const noexcept { return cached_index_; }
     /* ops of the whole gate list (compiled prefix + lowered tail) */
     std::vector<aqs_op> lower_all() const;
@@ -196,6 +221,8 @@ class QCircuit {
     uint32_t qubits_          = 0;
     std::size_t cached_index_ = 0;
     std::shared_ptr<std::vector<aqs_op>> compiled_ops_;
+    std::shared_ptr<std::vector<DenseGateRec>> compiled_dense_;   /* opaque matrices the markers in compiled_ops_ refer to */
+    std::shared_ptr<af::array> user_matrix_;                      /* write-through matrix of a gate-less circuit */
     mutable std::shared_ptr<detail::PlanCache> plan_;        /* compiled prefix */
     mutable std::shared_ptr<detail::PlanCache> tail_plan_;   /* last uncompiled tail that was simulated (reused while its ops do not change) */
     mutable std::shared_ptr<af::array> matrix_;

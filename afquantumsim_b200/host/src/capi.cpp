@@ -121,6 +121,16 @@ int aqsh_circuit_representation(void* c, char* buf, size_t cap, size_t* needed) 
     return copy_out(static_cast<QCircuit*>(c)->representation(), buf, cap, needed);
 }
 // lowered op list of the whole circuit (records are struct aqs_op, 64 bytes each)
+// opaque circuit: m = 2^n x 2^n complex64, ROW-major (numpy's default); stored column-major like af::array
+int aqsh_circuit_set_matrix(void* c, const float* m, uint32_t dim) {
+    return guarded([&] {
+        af::array a(static_cast<long long>(dim), static_cast<long long>(dim), af::c32);
+        for (uint32_t r = 0; r < dim; ++r)
+            for (uint32_t col = 0; col < dim; ++col)
+                a.data()[static_cast<std::size_t>(col) * dim + r] = af::cfloat{m[2 * (static_cast<std::size_t>(r) * dim + col)], m[2 * (static_cast<std::size_t>(r) * dim + col) + 1]};
+        static_cast<QCircuit*>(c)->set_matrix(a);
+    });
+}
 int aqsh_circuit_ops(void* c, void* out, uint64_t cap, uint64_t* count) {
     return guarded([&] {
         auto ops = static_cast<QCircuit*>(c)->lower_all();

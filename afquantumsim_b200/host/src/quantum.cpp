@@ -149,6 +149,19 @@ void OpSink::diag(uint32_t target, af::cfloat d0, af::cfloat d1, uint64_t ctrl_m
 void OpSink::x(uint32_t target, uint64_t ctrl_mask, uint64_t ctrl_value) {
     ops->push_back(blank_op(AQS_OP_X, target, ctrl_mask, ctrl_value));
 }
+void OpSink::dense_gate(uint32_t begin, uint32_t k, uint64_t ctrl_mask, const af::array& mc) {
+    if (!dense) throw std::logic_error{"this lowering context does not accept opaque matrices"};
+    const long long D = 1ll << k;
+    if (mc.dims(0) != D || mc.dims(1) != D) throw std::invalid_argument{"circuit matrix has the wrong shape"};
+    DenseGateRec r;
+    r.begin = begin; r.k = k; r.ctrl_mask = ctrl_mask;
+    r.m.resize(static_cast<std::size_t>(D * D));
+    for (long long row = 0; row < D; ++row)
+        for (long long col = 0; col < D; ++col) r.m[static_cast<std::size_t>(row * D + col)] = detail::c32(mc.data()[col * D + row]);
+    dense->push_back(std::move(r));
+    aqs_op op = blank_op(AQS_HOST_DENSE_MARK, static_cast<uint32_t>(dense->size() - 1), 0, 0);
+    ops->push_back(op);
+}
 void OpSink::swap(uint32_t a, uint32_t b, uint64_t ctrl_mask) {
     aqs_op op  = blank_op(AQS_OP_SWAP, a, ctrl_mask, ctrl_mask);
     op.target2 = static_cast<int32_t>(b);
@@ -203,7 +216,8 @@ void QState::force_normalize() {
 // QCircuit  (reference src/quantum.cpp:159-210)
 // ---------------------------------------------------------------------------
 QCircuit::QCircuit(uint32_t qubit_count)
-    : gate_list_{}, representation_{}, qubits_{qubit_count}, compiled_ops_{std::make_shared<std::vector<aqs_op>>()} {
+    : gate_list_{}, representation_{}, qubits_{qubit_count}, compiled_ops_{std::make_shared<std::vector<aqs_op>>()},
+      compiled_dense_{std::make_shared<std::vector<DenseGateRec>>()} {
     if (qubit_count < 1) throw std::invalid_argument{"Circuit must contain at least 1 qubit"};
     if (qubit_count > max_qubit_count)
         throw std::invalid_argument{"Maximum qubit count supported is " + std::to_string(max_qubit_count)};
@@ -211,6 +225,7 @@ QCircuit::QCircuit(uint32_t qubit_count)
 
 void QCircuit::detach() {
     if (compiled_ops_.use_count() > 1) compiled_ops_ = std::make_shared<std::vector<aqs_op>>(*compiled_ops_);
+    if (compiled_dense_.use_count() > 1) compiled_dense_ = std::make_shared<std::vector<DenseGateRec>>(*compiled_dense_);
     plan_.reset();
     tail_plan_.reset();
     matrix_.reset();
@@ -225,6 +240,7 @@ void QCircuit::clear() {
 void QCircuit::clear_cache() {
     cached_index_ = 0;
     compiled_ops_ = std::make_shared<std::vector<aqs_op>>();
+    compiled_dense_ = std::make_shared<std::vector<DenseGateRec>>();
     plan_.reset();
     tail_plan_.reset();
     matrix_.reset();
@@ -239,13 +255,52 @@ bool operator==(const QCircuit& lhs, const QCircuit& rhs) {
     return true;
 }
 
+namespace detail {
+static bool has_dense(const std::vector<aqs_op>& ops) {
+    for (const auto& op : ops)
+        if (op.kind == AQS_HOST_DENSE_MARK) return true;
+    return false;
+}
+// op list with opaque-matrix markers: fused plans for the runs of engine ops, aqs_apply_dense in between
+static void run_segments(aqs_state_t st, uint32_t n, const std::vector<aqs_op>& ops, const std::vector<DenseGateRec>& dense, uint32_t flags,
+                         uint32_t shift = 0) {
+    std::size_t i = 0;
+    while (i < ops.size()) {
+        std::size_t j = i;
+        while (j < ops.size() && ops[j].kind != AQS_HOST_DENSE_MARK) ++j;
+        if (j > i) {
+            PlanCache seg;
+            AQS_CALL(aqs_plan_build(static_cast<int>(n), ops.data() + i, j - i, flags, &seg.plan));
+            AQS_CALL(aqs_plan_run(st, seg.plan));
+            AQS_CALL(aqs_sync(st));
+        }
+        if (j < ops.size()) {
+            const DenseGateRec& r = dense.at(static_cast<std::size_t>(ops[j].target));
+            std::vector<int> q(r.k);
+            for (uint32_t t = 0; t < r.k; ++t) q[t] = static_cast<int>(r.begin + t + shift);
+            AQS_CALL(aqs_apply_dense(st, q.data(), static_cast<int>(r.k), r.ctrl_mask << shift, r.ctrl_mask << shift, r.m.data()));
+            ++j;
+        }
+        i = j;
+    }
+}
+}  // namespace detail
+
+void QCircuit::set_matrix(const af::array& m) {
+    if (!gate_list_.empty()) throw std::logic_error{"set_matrix: the circuit already has gates"};
+    if (qubits_ > 6) throw std::length_error{"set_matrix: opaque matrices of at most 6 qubits"};
+    const long long D = 1ll << qubits_;
+    if (m.dims(0) != D || m.dims(1) != D) throw std::invalid_argument{"set_matrix: the matrix must be 2^n x 2^n"};
+    user_matrix_ = std::make_shared<af::array>(m);
+}
+
 void QCircuit::compile() {
     if (cached_index_ != gate_list_.size()) {
         for (std::size_t i = cached_index_; i < gate_list_.size(); ++i) (*gate_list_[i])(*this);
         cached_index_ = gate_list_.size();
     }
     // the launch plan (and, on large states, its specialised kernels) is part of compiling
-    if (detail::g_engine_up && !compiled_ops_->empty() && (!plan_ || plan_->n_ops != compiled_ops_->size() || plan_->fused != detail::g_fusion)) {
+    if (detail::g_engine_up && !compiled_ops_->empty() && !detail::has_dense(*compiled_ops_) && (!plan_ || plan_->n_ops != compiled_ops_->size() || plan_->fused != detail::g_fusion)) {
         auto pc = std::make_shared<detail::PlanCache>();
         const uint32_t flags = (detail::g_fusion ? AQS_PLAN_FUSE : 0u) | detail::jit_flags(qubits_, true);
         AQS_CALL(aqs_plan_build(static_cast<int>(qubits_), compiled_ops_->data(), compiled_ops_->size(), flags, &pc->plan));
@@ -257,14 +312,18 @@ void QCircuit::compile() {
 
 std::vector<aqs_op> QCircuit::lower_all() const {
     std::vector<aqs_op> ops(*compiled_ops_);
-    OpSink sink{&ops, qubits_};
+    std::vector<DenseGateRec> dense(*compiled_dense_);
+    OpSink sink{&ops, qubits_, &dense};
     for (std::size_t i = cached_index_; i < gate_list_.size(); ++i) gate_list_[i]->lower(sink, 0, 0);
+    if (detail::has_dense(ops))
+        throw std::logic_error{"lower_all: the circuit holds opaque matrices, which engine op records cannot carry; use QSimulator::simulate"};
     return ops;
 }
 
 static constexpr uint32_t max_dense_qubits = 13;
 
 const af::array& QCircuit::circuit() const {
+    if (opaque()) return *user_matrix_;
     if (!matrix_) {
         if (qubits_ > max_dense_qubits)
             throw std::length_error{"circuit(): the dense matrix is only materialised for up to 13 qubits"};
@@ -280,14 +339,27 @@ const af::array& QCircuit::circuit() const {
             op.ctrl_mask <<= n;
             op.ctrl_value <<= n;
         }
-        AQS_CALL(aqs_apply_ops(dev.h, ops.data(), ops.size()));   // per-gate kernels: bit-reproducible
+        if (detail::has_dense(ops)) detail::run_segments(dev.h, 2 * n, ops, *compiled_dense_, 0u, n);
+        else AQS_CALL(aqs_apply_ops(dev.h, ops.data(), ops.size()));   // per-gate kernels: bit-reproducible
         auto m = std::make_shared<af::array>(static_cast<long long>(1) << n, static_cast<long long>(1) << n, af::c32);
         AQS_CALL(aqs_state_download(dev.h, reinterpret_cast<aqs_c32*>(m->data()), 0, 1ull << (2 * n)));
         matrix_ = m;
     }
     return *matrix_;
 }
-af::array& QCircuit::circuit() { return const_cast<af::array&>(static_cast<const QCircuit*>(this)->circuit()); }
+af::array& QCircuit::circuit() {
+    if (gate_list_.empty() && qubits_ <= 6) {
+        // write-through (see the header): the circuit owns this matrix; it starts as the identity
+        if (!user_matrix_) {
+            const long long D = 1ll << qubits_;
+            auto m = std::make_shared<af::array>(D, D, af::c32);
+            for (long long i = 0; i < D; ++i) m->data()[i * D + i] = af::cfloat{1.f, 0.f};
+            user_matrix_ = m;
+        }
+        return *user_matrix_;
+    }
+    return const_cast<af::array&>(static_cast<const QCircuit*>(this)->circuit());
+}
 
 // ---------------------------------------------------------------------------
 // QSimulator  (reference src/quantum.cpp:212-531)
@@ -365,9 +437,20 @@ void QSimulator::simulate(const QCircuit& circuit) {
         throw std::invalid_argument{"Number of qubit states and circuit input qubit states do not match"};
     const uint32_t flags = detail::g_fusion ? AQS_PLAN_FUSE : 0u;
 
+    if (circuit.opaque()) {
+        // the circuit IS a user-written matrix on all its qubits
+        std::vector<aqs_op> ops;
+        std::vector<DenseGateRec> dense;
+        OpSink sink{&ops, qubits_, &dense};
+        sink.dense_gate(0, qubits_, 0, *circuit.user_matrix());
+        detail::run_segments(dev_->h, qubits_, ops, dense, flags);
+        return;
+    }
     // compiled prefix: cached plan
     const auto& pre = circuit.compiled_ops();
-    if (!pre.empty()) {
+    if (!pre.empty() && detail::has_dense(pre)) {
+        detail::run_segments(dev_->h, qubits_, pre, circuit.compiled_dense(), flags | detail::jit_flags(qubits_, true));
+    } else if (!pre.empty()) {
         auto& pc = circuit.plan_;
         if (!pc || pc->n_ops != pre.size() || pc->fused != detail::g_fusion) {
             pc = std::make_shared<detail::PlanCache>();
@@ -380,10 +463,13 @@ void QSimulator::simulate(const QCircuit& circuit) {
     // uncompiled tail: lowered and planned now (gate parameters may have changed)
     if (circuit.cached_index_ < circuit.gate_list().size()) {
         std::vector<aqs_op> tail;
-        OpSink sink{&tail, qubits_};
+        std::vector<DenseGateRec> tail_dense;
+        OpSink sink{&tail, qubits_, &tail_dense};
         for (std::size_t i = circuit.cached_index_; i < circuit.gate_list().size(); ++i)
             circuit.gate_list()[i]->lower(sink, 0, 0);
-        if (!tail.empty()) {
+        if (!tail.empty() && detail::has_dense(tail)) {
+            detail::run_segments(dev_->h, qubits_, tail, tail_dense, flags | detail::jit_flags(qubits_, false));
+        } else if (!tail.empty()) {
             // the reference's own programs call simulate() on uncompiled circuits (benchmark/benchmark.cpp:18-28): the
             // plan of the last tail stays with the circuit and is reused while the lowered ops are the same
             const uint64_t h = detail::hash_ops(tail);
@@ -552,7 +638,7 @@ static inline uint64_t bit(uint32_t q) { return 1ull << q; }
 template<typename G>
 static QCircuit& compile_into(const G& g, QCircuit& qc) {
     g.check(qc);
-    OpSink sink{&qc.compiled_ops(), qc.qubit_count()};
+    OpSink sink{&qc.compiled_ops(), qc.qubit_count(), &qc.compiled_dense()};
     g.lower(sink, 0, 0);
     return qc;
 }
@@ -859,6 +945,7 @@ static std::string shift_statements(const std::string& text, uint32_t offset, bo
 }
 
 static std::shared_ptr<QCircuit> snapshot_circuit(const QCircuit& c) {
+    if (c.opaque()) return std::make_shared<QCircuit>(c);      // (no string representation to key the cache on)
     auto it = cached_circuits.find(c.representation());
     if (it == cached_circuits.end()) {
         it = cached_circuits.insert({c.representation(), std::make_shared<QCircuit>(c)}).first;
@@ -896,6 +983,7 @@ bool Gate::check(const QCircuit& qc) const {
 QCircuit& Gate::operator()(QCircuit& qc) const { return compile_into(*this, qc); }
 void Gate::lower(OpSink& k, uint32_t off, uint64_t cm) const {
     const QCircuit& in = *internal_circuit;
+    if (in.opaque()) { k.dense_gate(off + target_qubit_begin, in.qubit_count(), cm, *in.user_matrix()); return; }
     for (const auto& g : in.gate_list()) g->lower(k, off + target_qubit_begin, cm);
 }
 bool Gate::operator==(const QGate& rhs) const noexcept {
@@ -928,6 +1016,7 @@ QCircuit& ControlGate::operator()(QCircuit& qc) const { return compile_into(*thi
 void ControlGate::lower(OpSink& k, uint32_t off, uint64_t cm) const {
     const QCircuit& in = *internal_circuit;
     const uint64_t m   = cm | bit(control_qubit + off);
+    if (in.opaque()) { k.dense_gate(off + target_qubit_begin, in.qubit_count(), m, *in.user_matrix()); return; }
     for (const auto& g : in.gate_list()) g->lower(k, off + target_qubit_begin, m);
 }
 bool ControlGate::operator==(const QGate& rhs) const noexcept {

@@ -493,6 +493,9 @@ def run_ours(args):
                               "path": f"fused plan, {jr} of {ps} passes on specialised kernels", "ok": bool(rel < 1e-5)}
             assert rel < 1e-5, f"n = {n} parity against the oracle: rel L2 {rel}"
             del info["state"]
+        # the reference's own ALGORITHM (an explicit 2^n x 2^n operator per gate) at its own published sizes, same host cores
+        from oracle import ref_algorithm
+        line["cpu_baseline_ref_algorithm"] = ref_algorithm.published_sizes()
     if not args.no_configs:
         eng.pool_trim()
         line["configs"] = extra_configs(aqs, eng, wl, jit)

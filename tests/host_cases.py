@@ -456,6 +456,56 @@ def case_ghz16_profile():
     assert np.array_equal(qs.sample(u), want)
 
 
+def case_opaque_matrices_write_through():
+    """a user-written circuit matrix (reference: `qc.circuit() = M`, docs/USAGE.md:121-125) inside Gate / ControlGate,
+    compiled and uncompiled, against numpy on the oracle's states (reference src/quantum.cpp:1760-1814, 1888-1950)"""
+    from tests.dense_cases import dense_reference, random_unitary
+    aqs, orc, helpers = _mods()
+    rng = np.random.default_rng(77)
+    for n, k, b, ctrl in ((7, 3, 2, 0), (9, 5, 1, 8), (13, 6, 4, 1)):
+        U1, U2 = random_unitary(k, rng), random_unitary(k, rng)
+        pre = [("H", q) for q in range(n)] + [("CX", q, q + 1) for q in range(0, n - 1, 2)]
+        mid = [("RotY", q, 0.3 + 0.1 * q) for q in range(n)]
+        a = orc.simulate(orc.new_state(n), orc.Circ(n, pre))
+        a = dense_reference(a, n, list(range(b, b + k)), U1)
+        a = orc.simulate(a, orc.Circ(n, mid))
+        want = dense_reference(a, n, list(range(b, b + k)), U2, [ctrl])
+        for compiled in (False, True):
+            in1 = aqs.QCircuit(k).set_matrix(U1)
+            in2 = aqs.QCircuit(k).set_matrix(U2)
+            qc = aqs.QCircuit(n).extend(pre)
+            qc << aqs.Gate(in1, b)
+            qc.extend(mid)
+            qc << aqs.ControlGate(in2, ctrl, b)
+            if compiled:
+                qc.compile()
+            qs = aqs.QSimulator(n)
+            qs.simulate(qc)
+            err = orc.rel_l2(qs.statevector(), want)
+            assert err < 1e-5, (n, k, compiled, err)
+    # the opaque circuit simulated directly, and the errors of misuse
+    U = random_unitary(2, rng)
+    qs = aqs.QSimulator(2)
+    qs.simulate(aqs.QCircuit(2).set_matrix(U))
+    assert np.allclose(qs.statevector(), U[:, 0], atol=1e-6)
+    with pytest_raises(aqs.InvalidArgument):
+        aqs.QCircuit(2).set_matrix(np.eye(8))
+    with pytest_raises(aqs.EngineFailure):
+        (aqs.QCircuit(2) << aqs.H(0)).set_matrix(np.eye(4))
+
+
+class pytest_raises:
+    def __init__(self, exc):
+        self.exc = exc
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        assert et is not None and issubclass(et, self.exc), f"expected {self.exc.__name__}, got {et}"
+        return True
+
+
 ALL = [v for k, v in sorted(globals().items()) if k.startswith("case_")]
 
 

@@ -171,3 +171,15 @@ def test_closed_forms():
     assert abs(a[w] - (-1) ** k * np.sin((2 * k + 1) * th)) < 1e-4
     others = np.delete(a, w)
     assert np.max(np.abs(others - (-1) ** k * np.cos((2 * k + 1) * th) / np.sqrt((1 << n) - 1))) < 1e-4
+
+
+def test_reference_algorithm_restatement_matches_the_oracle():
+    """oracle/ref_algorithm.py (explicit CSR / dense-Kronecker operator per gate, what bench.py times as
+    cpu_baseline_ref_algorithm) computes the same states as the matrix-free oracle"""
+    from oracle import ref_algorithm as ra
+    a = ra.simulate(8, ra.qft(8))
+    assert orc.rel_l2(a, orc.simulate(orc.new_state(8), orc.fourier_transform(8))) < 1e-6
+    a = ra.simulate(7, ra.grover(7, 5, 3))
+    assert orc.rel_l2(a, orc.simulate(orc.new_state(7), orc.grover_search(7, orc.grover_oracle(7, 5), 3))) < 1e-6
+    a = ra.simulate(9, ra.ghz(9))
+    assert np.array_equal(a, orc.simulate(orc.new_state(9), orc.Circ(9, [("H", 0)] + [("CX", i, i + 1) for i in range(8)])))
