@@ -564,9 +564,11 @@ std::array<uint32_t, 2> QSimulator::profile_measure(uint32_t qubit, uint32_t rep
 }
 
 const af::array& QSimulator::statevector() const {
-    auto s = std::make_shared<af::array>(static_cast<long long>(state_count()), af::c32);
-    AQS_CALL(aqs_state_download(dev_->h, reinterpret_cast<aqs_c32*>(s->data()), 0, state_count()));
-    snapshot_ = s;
+    // One host buffer per simulator, refreshed in place: a reference obtained earlier stays valid (and shows the current
+    // state after the next call) instead of dangling, like the reference's member array (include/quantum.h:726-739).
+    if (!snapshot_ || snapshot_->elements() != static_cast<long long>(state_count()))
+        snapshot_ = std::make_shared<af::array>(static_cast<long long>(state_count()), af::c32);
+    AQS_CALL(aqs_state_download(dev_->h, reinterpret_cast<aqs_c32*>(snapshot_->data()), 0, state_count()));
     return *snapshot_;
 }
 af::array& QSimulator::statevector() { return const_cast<af::array&>(static_cast<const QSimulator*>(this)->statevector()); }

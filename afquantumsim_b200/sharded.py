@@ -557,8 +557,22 @@ class ShardedState:
             sch.exchange(pairs)
         return sch.finish()
 
+    def _bind_stream(self):
+        """The engine states follow torch's CURRENT stream (the torch ops, NCCL calls and stream-ordered barriers of this
+        class run there): re-bound at every entry point, so that a caller's `with torch.cuda.stream(...)` keeps kernels,
+        copies and collectives on one stream."""
+        if self.device.type != "cuda":
+            return
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != getattr(self, "_bound_stream", None):
+            self.state.set_stream(s)
+            if self.flat_state is not None:
+                self.flat_state.set_stream(s)
+            self._bound_stream = s
+
     def run(self, plan: ShardedPlan) -> None:
         """Execute a plan compiled for the current layout (asynchronous on the stream)."""
+        self._bind_stream()
         if self.pos != plan.entry_pos:
             raise ValueError("the plan was compiled for a different qubit layout; compile() again")
         for step in plan.steps:
@@ -770,6 +784,7 @@ class ShardedState:
 
     def sample(self, u: np.ndarray) -> np.ndarray:
         """Outcome index (64-bit) per uniform draw: first k with cumulative probability > u, 0 if none."""
+        self._bind_stream()
         self.canonicalize()
         U = fix62(u)
         mine = self.state.prob_fixed()
@@ -807,6 +822,7 @@ class ShardedState:
         return torch.cat(parts).cpu().numpy()
 
     def set_basis(self, index: int = 0):
+        self._bind_stream()
         self.buf.zero_()
         if (index >> self.n_local) == self.rank:
             self.buf[index & ((1 << self.n_local) - 1)] = 1.0

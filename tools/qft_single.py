@@ -12,7 +12,7 @@ from afquantumsim_b200 import workloads as wl  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 34
 eng.init(0)
 gates = wl.qft(n)
-plan = eng.Plan(n, wl.to_ops(gates), eng.PLAN_FUSE)
+plan = eng.Plan(n, wl.to_ops(gates), eng.PLAN_FUSE | eng.PLAN_JIT)
 s = eng.State(n)
 x = 0x2b3c4d5e6 & ((1 << n) - 1)
 t = eng.Timer()
