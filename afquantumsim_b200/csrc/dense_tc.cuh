@@ -12,11 +12,11 @@
 // 2^-22 relative).  That is 3 x 2 x 128 x 128 flops per group of 64 amplitudes = 1.65 TFLOP for a 2^30 state, under
 // the HBM time of the pass at tensor-core rates — the FP32 SIMT kernel (dense_kernels.cuh) needs 16.5 ms for it.
 //
-// One CTA (128 threads) per SM, persistent over tiles of 64 groups; the HBM loads of tile t + 1 are in flight (in registers)
+// One CTA (256 threads) per SM, persistent over tiles of 64 groups; the HBM loads of tile t + 1 are in flight (in registers)
 // while the MMAs of tile t run:
 //   * the matrix lives in TENSOR MEMORY for the whole kernel (operand A from TMEM: 128 lanes x 256 columns, hi and
 //     lo), written once with tcgen05.st;
-//   * per tile, every thread loads 32 amplitudes (lanes = consecutive groups: 256-byte runs), splits them and stores
+//   * per tile, every thread loads 16 amplitudes (lanes = consecutive groups: 256-byte runs), splits them and stores
 //     the hi / lo planes into shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core
 //     matrices: 16-byte chunk kc of row n at kc * 1024 + n * 16), one elected thread issues the 48 tcgen05.mma
 //     (K = 8 each) and commits them to an mbarrier;
@@ -28,7 +28,7 @@
 namespace aqs {
 
 constexpr int kTcGroups = 64;               // groups per tile = N of the MMA
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;             // 8 warps: two per quarter of the 128 tensor-memory lanes
 constexpr uint32_t kTcPlaneBytes = 32768;   // one operand plane (hi or lo) of a tile: 128 K x 64 N x 4 bytes
 constexpr uint32_t kTcStagePitch = 65;      // epilogue staging: float2 [group][65] (padded: conflict-free both ways)
 // Draining tile t - 1 while the MMAs of tile t run (double-buffered planes and accumulators) was measured SLOWER than
@@ -95,12 +95,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_tc(const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = (warp * 32u) << 16;                           // a warp reaches its own quarter of the 128 lanes
+    const uint32_t lane_base = ((warp & 3u) * 32u) << 16;                    // a warp reaches the quarter (warp % 4) of the 128 lanes
+    const uint32_t col_half = warp >> 2;                                     // the two warps of a quarter split the columns
 
     // ---- A = [[Mr, -Mi], [Mi, Mr]] into tensor memory: row m in lane m, K along the columns; hi at [0, 128), lo at [128, 256)
     {
-        const uint32_t part = tid >> 6, r = tid & 63u;
-        for (uint32_t c0 = 0; c0 < 128u; c0 += 16u) {
+        const uint32_t mrow = (warp & 3u) * 32u + (tid & 31u);
+        const uint32_t part = mrow >> 6, r = mrow & 63u;
+        for (uint32_t c0 = col_half * 64u; c0 < col_half * 64u + 64u; c0 += 16u) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (uint32_t j = 0; j < 16u; ++j) {
@@ -126,15 +128,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_tc(const __grid_constan
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcGroups >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t d_tmem = tmem + 256u;
     const uint32_t b_hi_addr = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_addr = (uint32_t)__cvta_generic_to_shared(b_lo);
-    const uint32_t gn = tid & 63u, h = tid >> 6;                              // this thread's group of the tile, and its half of the 64 elements
+    const uint32_t gn = tid & 63u, h = tid >> 6;                              // this thread's group of the tile, and its quarter of the 64 elements
     const uint32_t n_tiles = (uint32_t)(P.n_groups / kTcGroups);
     uint32_t phase[2] = {0u, 0u};
 
-    // this thread's 32 amplitudes of a tile: c = h * 32 + i
-    uint64_t coff[32];
+    // this thread's 16 amplitudes of a tile: c = h * 16 + i
+    uint64_t coff[16];
 #pragma unroll
-    for (uint32_t i = 0; i < 32u; ++i) {
-        const uint32_t c = h * 32u + i;
+    for (uint32_t i = 0; i < 16u; ++i) {
+        const uint32_t c = h * 16u + i;
         uint64_t off = 0;
 #pragma unroll
         for (int b = 0; b < 6; ++b)
@@ -142,11 +144,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_tc(const __grid_constan
         coff[i] = off;
     }
     auto tile_base = [&](uint32_t tile) { return P.a + (deposit_zeros((uint64_t)tile * kTcGroups + gn, P.fixed) | P.ctrl_or); };
-    float2 v[32];                                                             // the NEXT tile's inputs: loaded while this tile's MMAs run
+    float2 v[16];                                                             // the NEXT tile's inputs: loaded while this tile's MMAs run
     if (blockIdx.x < n_tiles) {
         const float2* b0 = tile_base(blockIdx.x);
 #pragma unroll
-        for (uint32_t i = 0; i < 32u; ++i) v[i] = b0[coff[i]];
+        for (uint32_t i = 0; i < 16u; ++i) v[i] = b0[coff[i]];
     }
 
     // Software pipeline over the tiles of this CTA, two stages deep: while the tensor core multiplies tile t (operand planes and
@@ -161,30 +163,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_tc(const __grid_constan
             phase[par] ^= 1u;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // D: row m = tid (lanes of this warp), 64 columns = the groups of the tile
-        uint32_t d[64];
+        // D: row m = (warp % 4) * 32 + lane, this warp's 32 of the 64 columns (= groups of the tile)
+        uint32_t d[32];
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
-            "%23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, "
-            "%52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+            "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
             : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]),
               "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]),
-              "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31]), "=r"(d[32]), "=r"(d[33]),
-              "=r"(d[34]), "=r"(d[35]), "=r"(d[36]), "=r"(d[37]), "=r"(d[38]), "=r"(d[39]), "=r"(d[40]), "=r"(d[41]), "=r"(d[42]), "=r"(d[43]), "=r"(d[44]),
-              "=r"(d[45]), "=r"(d[46]), "=r"(d[47]), "=r"(d[48]), "=r"(d[49]), "=r"(d[50]), "=r"(d[51]), "=r"(d[52]), "=r"(d[53]), "=r"(d[54]), "=r"(d[55]),
-              "=r"(d[56]), "=r"(d[57]), "=r"(d[58]), "=r"(d[59]), "=r"(d[60]), "=r"(d[61]), "=r"(d[62]), "=r"(d[63])
-            : "r"(d_tmem + par * 64u + lane_base) : "memory");
+              "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+            : "r"(d_tmem + par * 64u + col_half * 32u + lane_base) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         {
-            const uint32_t part = tid >> 6, r = tid & 63u;
+            const uint32_t mrow = (warp & 3u) * 32u + (tid & 31u);
+            const uint32_t part = mrow >> 6, r = mrow & 63u;
 #pragma unroll
-            for (uint32_t n = 0; n < 64u; ++n) stage[(n * kTcStagePitch + r) * 2u + part] = __uint_as_float(d[n]);
+            for (uint32_t j = 0; j < 32u; ++j) stage[((col_half * 32u + j) * kTcStagePitch + r) * 2u + part] = __uint_as_float(d[j]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
 #pragma unroll
-        for (uint32_t i = 0; i < 32u; ++i)
-            obase[coff[i]] = *reinterpret_cast<const float2*>(stage + (gn * kTcStagePitch + h * 32u + i) * 2u);
+        for (uint32_t i = 0; i < 16u; ++i)
+            obase[coff[i]] = *reinterpret_cast<const float2*>(stage + (gn * kTcStagePitch + h * 16u + i) * 2u);
     };
 
     uint32_t it = 0;
@@ -197,14 +196,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_tc(const __grid_constan
         // ---- B = [Re in; Im in]: this thread's 32 amplitudes, split, as 16-byte chunks of 4 consecutive K.  (The planes of this
         // parity were last read by the MMAs of tile t - 2, whose completion the epilogue of tile t - 2 has waited for.)
 #pragma unroll
-        for (uint32_t q = 0; q < 8u; ++q) {
+        for (uint32_t q = 0; q < 4u; ++q) {
             uint32_t rh[4], rl[4], ih[4], il[4];
 #pragma unroll
             for (uint32_t j = 0; j < 4u; ++j) {
                 tf32_split(v[q * 4u + j].x, rh[j], rl[j]);
                 tf32_split(v[q * 4u + j].y, ih[j], il[j]);
             }
-            const uint32_t kc = h * 8u + q;                                   // chunk of the real part; the imaginary part is 16 chunks on
+            const uint32_t kc = h * 4u + q;                                   // chunk of the real part; the imaginary part is 16 chunks on
             *reinterpret_cast<uint4*>(bh + (kc * 64u + gn) * 4u) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
             *reinterpret_cast<uint4*>(bl + (kc * 64u + gn) * 4u) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
             *reinterpret_cast<uint4*>(bh + ((16u + kc) * 64u + gn) * 4u) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
@@ -228,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_tc(const __grid_constan
         if (tile + gridDim.x < n_tiles) {                                     // next tile's inputs fly while the tensor core works
             const float2* nb = tile_base(tile + gridDim.x);
 #pragma unroll
-            for (uint32_t i = 0; i < 32u; ++i) v[i] = nb[coff[i]];
+            for (uint32_t i = 0; i < 16u; ++i) v[i] = nb[coff[i]];
         }
         if (kTcPipeline) {
             if (it) epilogue(par ^ 1u, prev_base);                            // tile t - 1, while the MMAs of tile t run

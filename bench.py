@@ -341,6 +341,8 @@ def run_ours(args):
         aqs.set_seed(30 + rank)
         return run_sharded(args, torch, dist, aqs, eng, wl, rank, world, local)
     torch.cuda.set_device(local)
+    in_tree = os.path.join(ROOT, "afquantumsim_b200", "lib", "libaqs_engine.so")
+    assert os.path.realpath(eng.LIB_PATH) == os.path.realpath(in_tree), "bench.py measures the in-tree engine only (AQS_ENGINE_LIB is for A/B builds)"
     sampler = ClockSampler(local).start()
     aqs.initialize(local)
     aqs.set_seed(30 + rank)

@@ -392,3 +392,18 @@ def test_sharded_pass_launches_cover_every_tile_once(n, g, seed):
     got = s.download()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert orc.rel_l2(got, orc.simulate(init.copy(), circ)) < TOL
+
+
+def test_sampling_many_draws_matches_oracle():
+    """10^5 draws on a 2^22 state (2^10 tile sums, one CTA per draw): bit-identical to the oracle on the same state"""
+    n = 22
+    circ = orc.Circ(n, wl.brickwork(n, 6))
+    s = eng.State(n)
+    s.run(eng.Plan(n, lower_array(circ), eng.PLAN_FUSE))
+    a = s.download()
+    u = np.random.default_rng(5).random(100000, dtype=np.float32)
+    assert np.array_equal(s.sample(u), orc.sample(a, u, "exact"))
+    idx, cnt = s.sample_hist_sparse(u)
+    want = np.bincount(orc.sample(a, u, "exact").astype(np.int64), minlength=1 << n)
+    assert int(cnt.sum()) == u.size and np.array_equal(want[idx.astype(np.int64)], cnt) and np.count_nonzero(want) == idx.size
+    s.close()
