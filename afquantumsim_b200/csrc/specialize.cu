@@ -975,6 +975,10 @@ struct Pool {
     std::condition_variable cv_work, cv_done;
     std::deque<std::shared_ptr<SpecKernel>> queue;
     std::unordered_map<uint64_t, std::shared_ptr<SpecKernel>> cache;
+    // passes seen before, by the hash of their launch descriptors (tile, layouts, ops with their coefficients): the same
+    // circuit planned again (every simulate() of an uncompiled circuit plans) skips source generation altogether
+    struct Memo { std::shared_ptr<SpecKernel> k; std::vector<uint64_t> coefs; };
+    std::unordered_map<uint64_t, Memo> memo;
     std::vector<std::thread> workers;
     size_t in_flight = 0;
     bool stop = false;
@@ -1034,8 +1038,54 @@ Pool& pool() {
 
 }  // namespace
 
+static uint64_t pass_descriptor_hash(int n, const FusedPass& fp) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    int minb = 0;
+    if (const char* e = std::getenv("AQS_JIT_MINB")) minb = std::atoi(e);
+    mix(&n, sizeof n); mix(&fp.T, sizeof fp.T); mix(&minb, sizeof minb);
+    mix(&fp.scale, sizeof fp.scale); mix(&fp.has_scale, sizeof fp.has_scale);
+    mix(fp.tile.pos, (size_t)fp.tile.n);
+    mix(fp.ld_toff, sizeof fp.ld_toff); mix(fp.ld_roff, sizeof fp.ld_roff); mix(fp.st_toff, sizeof fp.st_toff); mix(fp.st_roff, sizeof fp.st_roff);
+    if (!fp.segs.empty()) mix(fp.segs.data(), fp.segs.size() * sizeof(TileSeg));
+    if (!fp.ops.empty()) mix(fp.ops.data(), fp.ops.size() * sizeof(TileOp));
+    return h;
+}
+
 int spec_attach(int n, std::vector<FusedPass>& passes, bool wait) {
     Pool& pl = pool();
+    // 0. passes this process has specialised before (same descriptors, coefficients included)
+    std::vector<uint64_t> dkeys(passes.size());
+    {
+        bool all = !passes.empty();
+        std::vector<Pool::Memo> found(passes.size());
+        {
+            std::lock_guard<std::mutex> lk(pl.mu);
+            for (size_t i = 0; i < passes.size(); ++i) {
+                dkeys[i] = pass_descriptor_hash(n, passes[i]);
+                auto it = pl.memo.find(dkeys[i]);
+                if (it == pl.memo.end()) all = false;
+                else found[i] = it->second;
+            }
+            if (all) pl.hits += passes.size();
+        }
+        if (std::getenv("AQS_JIT_VERBOSE")) std::fprintf(stderr, "[aqs jit] attach: %zu passes, memo %s\n", passes.size(), all ? "hit" : "miss");
+        if (all) {
+            for (size_t i = 0; i < passes.size(); ++i) { passes[i].spec = found[i].k; passes[i].spec_coefs = found[i].coefs; }
+            if (wait) {
+                std::unique_lock<std::mutex> lk(pl.mu);
+                pl.cv_done.wait(lk, [&] {
+                    for (auto& f : found)
+                        if (f.k->state.load(std::memory_order_acquire) == SpecKernel::PENDING) return false;
+                    return true;
+                });
+            }
+            return AQS_OK;
+        }
+    }
     // 1. generate every pass's source; long circuits repeat their pass shapes (Grover-26, 64 iterations: 259 passes, 9 shapes)
     std::vector<SpecSource> srcs(passes.size());
     std::vector<char> have(passes.size(), 0);
@@ -1086,6 +1136,11 @@ int spec_attach(int n, std::vector<FusedPass>& passes, bool wait) {
         fp.spec = k;
         fp.spec_coefs = std::move(s.coefs);
         mine.push_back(k);
+        {
+            std::lock_guard<std::mutex> lk(pl.mu);
+            if (pl.memo.size() > 8192) pl.memo.clear();
+            pl.memo[dkeys[i]] = Pool::Memo{k, fp.spec_coefs};
+        }
     }
     if (wait) {
         std::unique_lock<std::mutex> lk(pl.mu);
