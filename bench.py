@@ -468,7 +468,7 @@ def run_ours(args):
                      "traffic_source": "ncu --set full capture committed under profiles/ (r02_spec_pass_ncu.txt), per launch; not re-measured in this run",
                      "peak_source": peak_src,
                      "note": "light passes of the specialised kernel run at the HBM floor (2.6 ms per pass), heavy ones are bound by the FP32 pipe "
-                             "(ncu: fma pipe 71 %, DESIGN.md 3.3); the HBM-bound per-gate kernels are under `unfused.roofline`",
+                             "(ncu on the heaviest: fma pipe 67 %, DRAM 26 %; on a light one: DRAM 76 %; DESIGN.md 3.3); the HBM-bound per-gate kernels are under `unfused.roofline`",
                      "kernel": ("specialised pass kernels (aqs_pass)" if jit_ready else "generic tile kernel (k_tile2)") if info_f["n_fused_passes"] else "per-gate kernels",
                      "algorithmic_bytes_per_step": info_f["bytes_planned"], "launches_per_step": info_f["n_launches"]},
         "generic_kernel": {"value": gate_apps / (ms_generic * 1e-3), "unit": "gate-apps/s", "ms_per_step": ms_generic, "gpu_launches": int(launches_g),
